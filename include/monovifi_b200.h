@@ -1,0 +1,93 @@
+/*
+ * libmonovifi_b200.so -- C ABI of the B200-native Mono-ViFI training inner loop (sm_100a).
+ *
+ * The reference (LiuJF1226/Mono-ViFI) is pure Python over torch; it has no FFI of its own.  The boundary
+ * below is what its `layers.py` / `train.py` call sites bind through ctypes (see INTEGRATION.md and
+ * mono_vifi_b200/_lib.py).  Each entry point names the reference code it replaces (paths relative to
+ * the reference checkout).
+ *
+ * Conventions
+ *   - every tensor pointer is a DEVICE pointer to a contiguous fp32 NCHW buffer owned by the caller
+ *     (a torch allocation); the library allocates nothing persistent;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream); all work is
+ *     enqueued on it, nothing synchronises;
+ *   - return value: 0 on success, negative mvf_status on failure; never throws, never exits;
+ *     mvf_last_error() returns a thread-local description of the last failure;
+ *   - `*_host` variants take HOST pointers and run H2D -> kernel -> D2H on the given stream, then
+ *     synchronise it (the end-to-end path a non-torch caller would use).
+ */
+#ifndef MONOVIFI_B200_H
+#define MONOVIFI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    MVF_OK = 0,
+    MVF_ERR_INVALID = -1, /* bad argument (null pointer, non-positive size, H or W < 3 ...) */
+    MVF_ERR_CUDA = -2,    /* a CUDA runtime call failed; see mvf_last_error() */
+    MVF_ERR_WORKSPACE = -3 /* workspace too small */
+} mvf_status;
+
+/* option flags: options.py:173-181 (no_ssim, avg_reprojection, disable_automasking) */
+#define MVF_NO_SSIM 1
+#define MVF_AVG_REPROJECTION 2
+#define MVF_DISABLE_AUTOMASKING 4
+
+typedef struct {
+    int B, H, W;
+    float min_disp;   /* (float)(1/max_depth)               layers.py:21 */
+    float disp_range; /* (float)(1/min_depth - 1/max_depth)  layers.py:22-23 */
+    float smooth_w;   /* opt.disparity_smoothness            train.py:1049 */
+    int flags;
+} mvf_f1_params;
+
+int mvf_version(void);
+const char* mvf_last_error(void);
+
+/* ---- fused view synthesis + photometric loss (F1) ------------------------------------------------
+ * Replaces, for one loss group (one target, two sources):
+ *   Trainer.generate_images_pred x2      train.py:956-971   (disp_to_depth layers.py:16-25,
+ *                                         BackprojectDepth layers.py:192-197, Project3D layers.py:211-222,
+ *                                         F.grid_sample border/align_corners=True)
+ *   Trainer.compute_reprojection_loss x4 train.py:973-985   (SSIM layers.py:277-290)
+ *   Trainer.compute_losses_base          train.py:987-1051  (get_smooth_loss layers.py:231-242)
+ *
+ * workspace: mvf_f1_workspace_bytes(B) bytes of device memory, zeroed ONCE with mvf_workspace_init and
+ * then reused by every call on the same stream (the kernels leave it zeroed).
+ */
+size_t mvf_f1_workspace_bytes(int B);
+int mvf_workspace_init(void* workspace, size_t bytes, void* stream);
+
+/* inputs : disp[B,1,H,W] tgt/src0/src1[B,3,H,W] inv_K[B,4,4] P0/P1[B,3,4] (= (K@T)[:, :3])
+ *          noise[B,nid,H,W] or NULL (nid = 2; 1 with avg_reprojection; the tensor train.py:1023 draws)
+ *          mask_rec[B,1,H,W] or NULL
+ * outputs: loss[4] = {loss, photometric mean, smoothness (unweighted), 0}
+ *          stats[B,4] (saved for backward), idx[B,H,W] uint8 argmin of `combined` (auto_mask = idx > 1)
+ * debug  : x0y0 int32 [2][2][B,H,W], warp0/warp1 [B,3,H,W], to_optimise [B,H,W]; all NULL in production */
+int mvf_f1_forward(const mvf_f1_params* p, const float* disp, const float* tgt, const float* src0,
+                   const float* src1, const float* inv_K, const float* P0, const float* P1, const float* noise,
+                   const float* mask_rec, float* loss, float* stats, uint8_t* idx, int32_t* x0y0, float* warp0,
+                   float* warp1, float* to_optimise, void* workspace, size_t workspace_bytes, void* stream);
+
+/* gradient of loss[0] w.r.t. disp and P0/P1 (the only inputs autograd needs: SURVEY.md 9.3).
+ * gout: device scalar dL/dloss or NULL (= 1).  idx/stats: as written by mvf_f1_forward. */
+int mvf_f1_backward(const mvf_f1_params* p, const float* disp, const float* tgt, const float* src0,
+                    const float* src1, const float* inv_K, const float* P0, const float* P1,
+                    const float* mask_rec, const uint8_t* idx, const float* stats, const float* gout,
+                    float* g_disp, float* g_P0, float* g_P1, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* host-buffer variant of the forward (allocates device scratch per call, synchronises) */
+int mvf_f1_forward_host(const mvf_f1_params* p, const float* disp, const float* tgt, const float* src0,
+                        const float* src1, const float* inv_K, const float* P0, const float* P1,
+                        const float* noise, const float* mask_rec, float* loss, uint8_t* idx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,62 @@
+"""ctypes binding of libmonovifi_b200.so (include/monovifi_b200.h).  Fails loudly when the library is missing."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libmonovifi_b200.so")
+
+NO_SSIM, AVG_REPROJECTION, DISABLE_AUTOMASKING = 1, 2, 4
+
+
+class F1Params(ctypes.Structure):
+    _fields_ = [("B", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("min_disp", ctypes.c_float),
+                ("disp_range", ctypes.c_float), ("smooth_w", ctypes.c_float), ("flags", ctypes.c_int)]
+
+
+_vp, _sz, _i, _f = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float
+_P = ctypes.POINTER(F1Params)
+
+# name -> (restype, argtypes); every symbol include/monovifi_b200.h declares
+SIGNATURES = {
+    "mvf_version": (_i, []),
+    "mvf_last_error": (ctypes.c_char_p, []),
+    "mvf_f1_workspace_bytes": (_sz, [_i]),
+    "mvf_workspace_init": (_i, [_vp, _sz, _vp]),
+    "mvf_f1_forward": (_i, [_P] + [_vp] * 16 + [_vp, _sz, _vp]),
+    "mvf_f1_backward": (_i, [_P] + [_vp] * 14 + [_vp, _sz, _vp]),
+    "mvf_f1_forward_host": (_i, [_P] + [_vp] * 11),
+}
+
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise LibraryMissing(
+                "%s not found: build it with `python -m mono_vifi_b200.build` (nvcc, sm_100a). "
+                "There is no CPU / PyTorch fallback for these ops." % SO_PATH)
+        l = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise RuntimeError("libmonovifi_b200 %s failed (%d): %s" % (what, rc, lib().mvf_last_error().decode()))
+
+
+def f1_params(B, H, W, min_depth=0.1, max_depth=100.0, smooth_w=1e-3, flags=0):
+    """python-double arithmetic then one cast to fp32, exactly what layers.py:21-23 hands to torch."""
+    min_disp = 1 / max_depth
+    max_disp = 1 / min_depth
+    return F1Params(B, H, W, min_disp, max_disp - min_disp, smooth_w, flags)

@@ -1,0 +1,141 @@
+// C ABI of libmonovifi_b200.so (include/monovifi_b200.h).  Plain pointers and sizes only.
+#include "../../include/monovifi_b200.h"
+
+#include <cstdio>
+#include <cstring>
+
+#include "f1.cuh"
+#include "ops.cuh"
+
+namespace {
+thread_local char g_err[512] = "";
+
+int fail(mvf_status st, const char* what, cudaError_t e = cudaSuccess) {
+    if (e != cudaSuccess)
+        snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    else
+        snprintf(g_err, sizeof(g_err), "%s", what);
+    return (int)st;
+}
+
+bool fill_args(mvf::F1Args& a, const mvf_f1_params* p) {
+    if (!p || p->B <= 0 || p->H < 3 || p->W < 3) return false;
+    a.B = p->B;
+    a.H = p->H;
+    a.W = p->W;
+    a.min_disp = p->min_disp;
+    a.disp_range = p->disp_range;
+    a.smooth_w = p->smooth_w;
+    a.flags = p->flags;
+    return true;
+}
+}  // namespace
+
+extern "C" {
+
+int mvf_version(void) { return 100; }
+const char* mvf_last_error(void) { return g_err; }
+
+size_t mvf_f1_workspace_bytes(int B) { return B > 0 ? mvf::f1_workspace_bytes(B) : 0; }
+
+int mvf_workspace_init(void* workspace, size_t bytes, void* stream) {
+    if (!workspace || bytes == 0) return fail(MVF_ERR_INVALID, "mvf_workspace_init: null workspace");
+    cudaError_t e = cudaMemsetAsync(workspace, 0, bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(MVF_ERR_CUDA, "mvf_workspace_init", e);
+    return MVF_OK;
+}
+
+int mvf_f1_forward(const mvf_f1_params* p, const float* disp, const float* tgt, const float* src0,
+                   const float* src1, const float* inv_K, const float* P0, const float* P1, const float* noise,
+                   const float* mask_rec, float* loss, float* stats, uint8_t* idx, int32_t* x0y0, float* warp0,
+                   float* warp1, float* to_optimise, void* workspace, size_t workspace_bytes, void* stream) {
+    mvf::F1Args a;
+    memset(&a, 0, sizeof(a));
+    if (!fill_args(a, p)) return fail(MVF_ERR_INVALID, "mvf_f1_forward: bad params (need B>0, H>=3, W>=3)");
+    if (!disp || !tgt || !src0 || !src1 || !inv_K || !P0 || !P1 || !loss || !stats || !idx)
+        return fail(MVF_ERR_INVALID, "mvf_f1_forward: null required pointer");
+    if (x0y0 && (!warp0 || !warp1)) return fail(MVF_ERR_INVALID, "mvf_f1_forward: x0y0 needs warp0/warp1");
+    if (!workspace || workspace_bytes < mvf::f1_workspace_bytes(p->B))
+        return fail(MVF_ERR_WORKSPACE, "mvf_f1_forward: workspace too small");
+    a.disp = disp; a.tgt = tgt; a.src0 = src0; a.src1 = src1; a.inv_K = inv_K; a.P0 = P0; a.P1 = P1;
+    a.noise = noise; a.mask = mask_rec; a.loss = loss; a.stats = stats; a.idx = idx;
+    a.x0y0 = x0y0; a.warp0 = warp0; a.warp1 = warp1; a.to_opt = to_optimise;
+    a.ws = (mvf::F1Workspace*)workspace;
+    cudaError_t e = mvf::launch_f1_forward(a, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(MVF_ERR_CUDA, "mvf_f1_forward launch", e);
+    return MVF_OK;
+}
+
+int mvf_f1_backward(const mvf_f1_params* p, const float* disp, const float* tgt, const float* src0,
+                    const float* src1, const float* inv_K, const float* P0, const float* P1,
+                    const float* mask_rec, const uint8_t* idx, const float* stats, const float* gout,
+                    float* g_disp, float* g_P0, float* g_P1, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+    mvf::F1Args a;
+    memset(&a, 0, sizeof(a));
+    if (!fill_args(a, p)) return fail(MVF_ERR_INVALID, "mvf_f1_backward: bad params (need B>0, H>=3, W>=3)");
+    if (!disp || !tgt || !src0 || !src1 || !inv_K || !P0 || !P1 || !idx || !stats || !g_disp || !g_P0 || !g_P1)
+        return fail(MVF_ERR_INVALID, "mvf_f1_backward: null required pointer");
+    if (!workspace || workspace_bytes < mvf::f1_workspace_bytes(p->B))
+        return fail(MVF_ERR_WORKSPACE, "mvf_f1_backward: workspace too small");
+    a.disp = disp; a.tgt = tgt; a.src0 = src0; a.src1 = src1; a.inv_K = inv_K; a.P0 = P0; a.P1 = P1;
+    a.mask = mask_rec; a.idx = const_cast<uint8_t*>(idx); a.stats = const_cast<float*>(stats); a.gout = gout;
+    a.g_disp = g_disp; a.g_P0 = g_P0; a.g_P1 = g_P1;
+    a.ws = (mvf::F1Workspace*)workspace;
+    cudaError_t e = mvf::launch_f1_backward(a, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(MVF_ERR_CUDA, "mvf_f1_backward launch", e);
+    return MVF_OK;
+}
+
+int mvf_f1_forward_host(const mvf_f1_params* p, const float* disp, const float* tgt, const float* src0,
+                        const float* src1, const float* inv_K, const float* P0, const float* P1,
+                        const float* noise, const float* mask_rec, float* loss, uint8_t* idx) {
+    if (!p || p->B <= 0 || p->H < 3 || p->W < 3) return fail(MVF_ERR_INVALID, "mvf_f1_forward_host: bad params");
+    if (!disp || !tgt || !src0 || !src1 || !inv_K || !P0 || !P1 || !loss)
+        return fail(MVF_ERR_INVALID, "mvf_f1_forward_host: null required pointer");
+    const size_t n = (size_t)p->B * p->H * p->W;
+    const bool avg = p->flags & MVF_AVG_REPROJECTION, am = !(p->flags & MVF_DISABLE_AUTOMASKING);
+    const size_t nid = am ? (avg ? 1 : 2) : 0;
+    const size_t fl = n * (1 + 9 + (noise ? nid : 0) + (mask_rec ? 1 : 0)) + (size_t)p->B * (16 + 24 + 4) + 4;
+    const size_t wsb = mvf::f1_workspace_bytes(p->B);
+    char* base = nullptr;
+    cudaError_t e = cudaMalloc(&base, fl * sizeof(float) + n + wsb + 256);
+    if (e != cudaSuccess) return fail(MVF_ERR_CUDA, "mvf_f1_forward_host: cudaMalloc", e);
+    cudaStream_t st = 0;
+    float* f = (float*)base;
+    auto put = [&](const float* h, size_t cnt) -> float* {
+        float* d = f;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d, h, cnt * sizeof(float), cudaMemcpyHostToDevice, st);
+        f += cnt;
+        return d;
+    };
+    float* d_disp = put(disp, n);
+    float* d_tgt = put(tgt, 3 * n);
+    float* d_s0 = put(src0, 3 * n);
+    float* d_s1 = put(src1, 3 * n);
+    float* d_noise = (noise && nid) ? put(noise, nid * n) : nullptr;
+    float* d_mask = mask_rec ? put(mask_rec, n) : nullptr;
+    float* d_ik = put(inv_K, 16 * (size_t)p->B);
+    float* d_p0 = put(P0, 12 * (size_t)p->B);
+    float* d_p1 = put(P1, 12 * (size_t)p->B);
+    float* d_stats = f; f += 4 * (size_t)p->B;
+    float* d_loss = f; f += 4;
+    uint8_t* d_idx = (uint8_t*)f;
+    void* d_ws = (void*)(((uintptr_t)(d_idx + n) + 255) & ~(uintptr_t)255);
+    int rc = MVF_OK;
+    if (e != cudaSuccess) rc = fail(MVF_ERR_CUDA, "mvf_f1_forward_host: H2D", e);
+    if (rc == MVF_OK) rc = mvf_workspace_init(d_ws, wsb, st);
+    if (rc == MVF_OK)
+        rc = mvf_f1_forward(p, d_disp, d_tgt, d_s0, d_s1, d_ik, d_p0, d_p1, d_noise, d_mask, d_loss, d_stats, d_idx,
+                            nullptr, nullptr, nullptr, nullptr, d_ws, wsb, st);
+    if (rc == MVF_OK) {
+        e = cudaMemcpyAsync(loss, d_loss, 4 * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && idx) e = cudaMemcpyAsync(idx, d_idx, n, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(MVF_ERR_CUDA, "mvf_f1_forward_host: D2H", e);
+    }
+    cudaFree(base);
+    return rc;
+}
+
+}  // extern "C"

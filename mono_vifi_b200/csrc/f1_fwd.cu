@@ -1,0 +1,330 @@
+// F1 forward: one fused HBM-bound kernel for
+//   disp_to_depth -> BackprojectDepth -> Project3D -> grid_sample(border, align_corners) of 2 sources
+//   -> 4x (SSIM + L1) -> +noise -> per-pixel min / argmin -> (mask) -> mean, plus edge-aware smoothness.
+// Reference lines: layers.py:16-25, 192-197, 211-222, 231-242, 277-290; train.py:956-1051.
+//
+// Tiling: one CTA per 32x16 output tile of one image.  Phase 1 computes the two warped sources at the
+// tile + 1px reflection halo and stages them, with the target and the raw sources, in shared memory
+// (identity/warped candidates interleaved as float2 so the window statistics run on packed FFMA2).
+// Phase 2 (one 64-thread group per colour channel) evaluates the separable 3x3 window sums: each thread
+// owns 2 columns x 4 rows, horizontal sums from 128-bit LDS, vertical sums from a register ring.
+// Phase 3 mixes channels, takes min/argmin, adds smoothness and reduces.  Algorithmic HBM traffic:
+// 40 B/px read (+8 noise, +4 mask), 1 B/px written (argmin map for the backward).
+#include "f1.cuh"
+
+namespace mvf {
+
+namespace {
+
+constexpr int TW = 32, TH = 16;
+constexpr int HWD = TW + 2, HHT = TH + 2;
+constexpr int NT = 192;  // 3 channel groups x 64 threads
+constexpr int RPT = 4;   // output rows per thread in phase 2
+
+struct __align__(16) FwdSmem {
+    float2 T2[3][HHT][HWD];  // target, duplicated {t,t}
+    float2 S[3][HHT][HWD];   // raw sources {src0, src1}   (identity-reprojection candidates)
+    float2 Wp[3][HHT][HWD];  // warped sources {warp0, warp1}
+    float4 REP[3][TH][TW];   // per-channel reprojection terms {id0, id1, w0, w1}
+    float D[TH + 1][TW + 1]; // disparity (+1 right / bottom neighbour for the smoothness term)
+    float cst[36];           // inv_K rows 0..2 (12), P0 (12), P1 (12)
+    float red[NT / 32][4];
+    int is_last;
+};
+
+struct HS {  // horizontal 3-tap sums for one output column
+    float2 t, tt, s, ss, st, w, ww, wt;
+};
+
+__device__ __forceinline__ void hsum_pair(float2 x0, float2 x1, float2 x2, float2 x3, float2 t0, float2 t1,
+                                          float2 t2, float2 t3, float2& a0, float2& a1, float2& b0, float2& b1,
+                                          float2& c0, float2& c1) {
+    float2 m = add2(x1, x2);
+    a0 = add2(m, x0);
+    a1 = add2(m, x3);
+    m = fma2(x1, x1, mul2(x2, x2));
+    b0 = fma2(x0, x0, m);
+    b1 = fma2(x3, x3, m);
+    m = fma2(x1, t1, mul2(x2, t2));
+    c0 = fma2(x0, t0, m);
+    c1 = fma2(x3, t3, m);
+}
+
+__device__ __forceinline__ void hsum_row(const FwdSmem& sm, int c, int hr, int cx, HS h[2], float2 ctr[6]) {
+    const float4* tp = reinterpret_cast<const float4*>(&sm.T2[c][hr][2 * cx]);
+    const float4* sp = reinterpret_cast<const float4*>(&sm.S[c][hr][2 * cx]);
+    const float4* wp = reinterpret_cast<const float4*>(&sm.Wp[c][hr][2 * cx]);
+    float4 ta = tp[0], tb = tp[1], sa = sp[0], sb = sp[1], wa = wp[0], wb = wp[1];
+    float2 t0 = make_float2(ta.x, ta.y), t1 = make_float2(ta.z, ta.w), t2 = make_float2(tb.x, tb.y),
+           t3 = make_float2(tb.z, tb.w);
+    float2 s0 = make_float2(sa.x, sa.y), s1 = make_float2(sa.z, sa.w), s2 = make_float2(sb.x, sb.y),
+           s3 = make_float2(sb.z, sb.w);
+    float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w), w2 = make_float2(wb.x, wb.y),
+           w3 = make_float2(wb.z, wb.w);
+    float2 m = add2(t1, t2);
+    h[0].t = add2(m, t0);
+    h[1].t = add2(m, t3);
+    m = fma2(t1, t1, mul2(t2, t2));
+    h[0].tt = fma2(t0, t0, m);
+    h[1].tt = fma2(t3, t3, m);
+    hsum_pair(s0, s1, s2, s3, t0, t1, t2, t3, h[0].s, h[1].s, h[0].ss, h[1].ss, h[0].st, h[1].st);
+    hsum_pair(w0, w1, w2, w3, t0, t1, t2, t3, h[0].w, h[1].w, h[0].ww, h[1].ww, h[0].wt, h[1].wt);
+    ctr[0] = t1; ctr[1] = t2; ctr[2] = s1; ctr[3] = s2; ctr[4] = w1; ctr[5] = w2;
+}
+
+// 0.85/3 * SSIM-loss + 0.15/3 * |t - x| for a packed pair of candidates (layers.py:277-290, train.py:973-985)
+__device__ __forceinline__ float2 rep_pair(float2 vx, float2 vxx, float2 vxt, float2 my, float2 my2c, float2 sigyc,
+                                           float2 tc, float2 xc, float cS, float cL) {
+    const float2 k9 = f2(1.0f / 9.0f);
+    const float C1 = 0.0001f, C2 = 0.0009f;
+    float2 mx = mul2(vx, k9);
+    float2 mxmy = mul2(mx, my);
+    float2 mx2 = mul2(mx, mx);
+    float2 sigx = fma2(vxx, k9, -mx2);
+    float2 sigxy = fma2(vxt, k9, -mxmy);
+    float2 n = mul2(fma2(f2(2.0f), mxmy, f2(C1)), fma2(f2(2.0f), sigxy, f2(C2)));
+    float2 d = mul2(add2(mx2, my2c), add2(sigx, sigyc));
+    float2 df = sub2(tc, xc);
+    float2 r;
+    r.x = __saturatef(fmaf(-0.5f, __fdividef(n.x, d.x), 0.5f));
+    r.y = __saturatef(fmaf(-0.5f, __fdividef(n.y, d.y), 0.5f));
+    r.x = fmaf(cL, fabsf(df.x), cS * r.x);
+    r.y = fmaf(cL, fabsf(df.y), cS * r.y);
+    return r;
+}
+
+__device__ __forceinline__ void emit(FwdSmem& sm, int c, int orow, int cx, const HS a[2], const HS b[2], const HS cu[2],
+                                     const float2 ctr[6], float cS, float cL) {
+    const float2 k9 = f2(1.0f / 9.0f);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        float2 vt = add2(add2(a[j].t, b[j].t), cu[j].t);
+        float2 vtt = add2(add2(a[j].tt, b[j].tt), cu[j].tt);
+        float2 my = mul2(vt, k9);
+        float2 my2 = mul2(my, my);
+        float2 sigyc = add2(fma2(vtt, k9, -my2), f2(0.0009f));
+        float2 my2c = add2(my2, f2(0.0001f));
+        float2 vs = add2(add2(a[j].s, b[j].s), cu[j].s);
+        float2 vss = add2(add2(a[j].ss, b[j].ss), cu[j].ss);
+        float2 vst = add2(add2(a[j].st, b[j].st), cu[j].st);
+        float2 vw = add2(add2(a[j].w, b[j].w), cu[j].w);
+        float2 vww = add2(add2(a[j].ww, b[j].ww), cu[j].ww);
+        float2 vwt = add2(add2(a[j].wt, b[j].wt), cu[j].wt);
+        float2 rs = rep_pair(vs, vss, vst, my, my2c, sigyc, ctr[j], ctr[2 + j], cS, cL);
+        float2 rw = rep_pair(vw, vww, vwt, my, my2c, sigyc, ctr[j], ctr[4 + j], cS, cL);
+        sm.REP[c][orow][2 * cx + j] = make_float4(rs.x, rs.y, rw.x, rw.y);
+    }
+}
+
+__global__ void __launch_bounds__(NT, 2) f1_fwd_kernel(const F1Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z, tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    const int H = a.H, W = a.W;
+    const size_t HW = (size_t)H * W;
+
+    if (tid < 12) sm.cst[tid] = a.inv_K[16 * b + tid];
+    else if (tid < 24) sm.cst[tid] = a.P0[12 * b + tid - 12];
+    else if (tid < 36) sm.cst[tid] = a.P1[12 * b + tid - 24];
+    __syncthreads();
+
+    // ---------------- phase 1: view synthesis at tile + halo, stage everything in shared memory -------------
+    {
+        const Geo g = make_geo(H, W);
+        const float* dispb = a.disp + (size_t)b * HW;
+        const float* tgtb = a.tgt + (size_t)b * 3 * HW;
+        const float* s0b = a.src0 + (size_t)b * 3 * HW;
+        const float* s1b = a.src1 + (size_t)b * 3 * HW;
+        for (int p = tid; p < HHT * HWD; p += NT) {
+            int hy = p / HWD, hx = p - hy * HWD;
+            int ry = ty0 - 1 + hy, rx = tx0 - 1 + hx;          // raw (possibly padded / out-of-image) coords
+            int y = clampi(reflect1(ry, H), 0, H - 1), x = clampi(reflect1(rx, W), 0, W - 1);
+            size_t i = (size_t)y * W + x;
+            float d = __ldg(dispb + i);
+            float tv[3], sv0[3], sv1[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                tv[c] = __ldg(tgtb + c * HW + i);
+                sv0[c] = __ldg(s0b + c * HW + i);
+                sv1[c] = __ldg(s1b + c * HW + i);
+            }
+            float depth = disp_to_depth(d, a.min_disp, a.disp_range);
+            float cr[3], X[3], pr[3];
+            cam_ray(sm.cst, (float)x, (float)y, cr);
+            Tap t0, t1;
+            project_tap(depth, cr, sm.cst + 12, g, t0, X, pr);
+            project_tap(depth, cr, sm.cst + 24, g, t1, X, pr);
+            float w0[3], w1[3];
+            bilinear3(s0b, H, W, t0, w0);
+            bilinear3(s1b, H, W, t1, w1);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                sm.T2[c][hy][hx] = make_float2(tv[c], tv[c]);
+                sm.S[c][hy][hx] = make_float2(sv0[c], sv1[c]);
+                sm.Wp[c][hy][hx] = make_float2(w0[c], w1[c]);
+            }
+            if (hy >= 1 && hx >= 1) sm.D[hy - 1][hx - 1] = d;
+            if (a.x0y0 != nullptr && ry == y && rx == x && hy >= 1 && hy <= TH && hx >= 1 && hx <= TW) {
+                size_t n = (size_t)a.B * HW, o = (size_t)b * HW + i;
+                a.x0y0[o] = t0.x0;
+                a.x0y0[n + o] = t0.y0;
+                a.x0y0[2 * n + o] = t1.x0;
+                a.x0y0[3 * n + o] = t1.y0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    a.warp0[((size_t)b * 3 + c) * HW + i] = w0[c];
+                    a.warp1[((size_t)b * 3 + c) * HW + i] = w1[c];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: separable 3x3 window statistics, SSIM + L1 per channel ------------------------
+    {
+        const bool nossim = (a.flags & F_NO_SSIM) != 0;
+        const float cS = nossim ? 0.0f : 0.85f / 3.0f, cL = nossim ? 1.0f / 3.0f : 0.15f / 3.0f;
+        const int c = tid >> 6, t = tid & 63, cx = t & 15, rg = t >> 4;
+        HS r0[2], r1[2], cu[2];
+        float2 ctr_prev[6], ctr[6];
+        hsum_row(sm, c, rg * RPT + 0, cx, r0, ctr);
+        hsum_row(sm, c, rg * RPT + 1, cx, r1, ctr_prev);
+#pragma unroll
+        for (int s = 2; s < RPT + 2; ++s) {
+            hsum_row(sm, c, rg * RPT + s, cx, cu, ctr);
+            emit(sm, c, rg * RPT + s - 2, cx, r0, r1, cu, ctr_prev, cS, cL);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { r0[j] = r1[j]; r1[j] = cu[j]; }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) ctr_prev[q] = ctr[q];
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 3: channel mix, min / argmin, mask, smoothness, reduction ------------------------
+    float photo = 0.f, sx = 0.f, sy = 0.f, sd = 0.f;
+    {
+        const bool avg = (a.flags & F_AVG_REPROJECTION) != 0, am = !(a.flags & F_DISABLE_AUTOMASKING);
+        const int nid = am ? (avg ? 1 : 2) : 0;
+        for (int p = tid; p < TW * TH; p += NT) {
+            int row = p / TW, col = p - row * TW;
+            int y = ty0 + row, x = tx0 + col;
+            if (y >= H || x >= W) continue;
+            size_t i = (size_t)y * W + x;
+            float4 r0 = sm.REP[0][row][col], r1 = sm.REP[1][row][col], r2 = sm.REP[2][row][col];
+            float id0 = r0.x + r1.x + r2.x, id1 = r0.y + r1.y + r2.y;
+            float w0 = r0.z + r1.z + r2.z, w1 = r0.w + r1.w + r2.w;
+            float comb[4];
+            int nc = 0;
+            if (am) {
+                const float* nz = a.noise ? a.noise + (size_t)b * nid * HW + i : nullptr;
+                if (avg) {
+                    comb[nc++] = (id0 + id1) * 0.5f + (nz ? __ldg(nz) * 0.00001f : 0.f);
+                } else {
+                    comb[nc++] = id0 + (nz ? __ldg(nz) * 0.00001f : 0.f);
+                    comb[nc++] = id1 + (nz ? __ldg(nz + HW) * 0.00001f : 0.f);
+                }
+            }
+            if (avg) {
+                comb[nc++] = (w0 + w1) * 0.5f;
+            } else {
+                comb[nc++] = w0;
+                comb[nc++] = w1;
+            }
+            int best = 0;
+            float m = comb[0];
+            for (int q = 1; q < nc; ++q)
+                if (comb[q] < m) { m = comb[q]; best = q; }
+            if (a.mask) m *= __ldg(a.mask + (size_t)b * HW + i);
+            a.idx[(size_t)b * HW + i] = (uint8_t)best;
+            if (a.to_opt) a.to_opt[(size_t)b * HW + i] = m;
+            photo += m;
+            // edge-aware smoothness on the raw disparity; the 1/(mean+eps) factor is applied per image later
+            float d = sm.D[row][col];
+            sd += d;
+            if (x + 1 < W) {
+                float gi = fabsf(sm.T2[0][row + 1][col + 1].x - sm.T2[0][row + 1][col + 2].x) +
+                           fabsf(sm.T2[1][row + 1][col + 1].x - sm.T2[1][row + 1][col + 2].x) +
+                           fabsf(sm.T2[2][row + 1][col + 1].x - sm.T2[2][row + 1][col + 2].x);
+                sx += fabsf(d - sm.D[row][col + 1]) * __expf(-(gi / 3.0f));
+            }
+            if (y + 1 < H) {
+                float gi = fabsf(sm.T2[0][row + 1][col + 1].x - sm.T2[0][row + 2][col + 1].x) +
+                           fabsf(sm.T2[1][row + 1][col + 1].x - sm.T2[1][row + 2][col + 1].x) +
+                           fabsf(sm.T2[2][row + 1][col + 1].x - sm.T2[2][row + 2][col + 1].x);
+                sy += fabsf(d - sm.D[row + 1][col]) * __expf(-(gi / 3.0f));
+            }
+        }
+    }
+    photo = warp_sum(photo);
+    sx = warp_sum(sx);
+    sy = warp_sum(sy);
+    sd = warp_sum(sd);
+    if ((tid & 31) == 0) {
+        sm.red[tid >> 5][0] = photo;
+        sm.red[tid >> 5][1] = sx;
+        sm.red[tid >> 5][2] = sy;
+        sm.red[tid >> 5][3] = sd;
+    }
+    __syncthreads();
+    long long* acc = ws_fwd_acc(a.ws);
+    if (tid < 4) {
+        double v = 0;
+        for (int w = 0; w < NT / 32; ++w) v += (double)sm.red[w][tid];
+        atomicAdd(reinterpret_cast<unsigned long long*>(acc + 4 * b + tid), (unsigned long long)to_fix(v));
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        unsigned int ticket = atomicAdd(&a.ws->counter_fwd, 1u);
+        sm.is_last = (ticket == total - 1);
+    }
+    __syncthreads();
+    if (sm.is_last && tid == 0) {
+        __threadfence();
+        const int B = a.B;
+        double photo_t = 0, smx = 0, smy = 0;
+        for (int bb = 0; bb < B; ++bb) {
+            volatile long long* v = acc + 4 * bb;
+            double ph = from_fix(v[0]), Sx = from_fix(v[1]), Sy = from_fix(v[2]), Sd = from_fix(v[3]);
+            v[0] = 0; v[1] = 0; v[2] = 0; v[3] = 0;
+            float mean = (float)(Sd / (double)HW);
+            double den = (double)(mean + 1e-7f);
+            photo_t += ph;
+            smx += Sx / den;
+            smy += Sy / den;
+            a.stats[4 * bb + 0] = mean;
+            a.stats[4 * bb + 1] = (float)Sx;
+            a.stats[4 * bb + 2] = (float)Sy;
+            a.stats[4 * bb + 3] = 0.f;
+        }
+        double n = (double)B * (double)HW;
+        double ph = photo_t / n;
+        double smooth = smx / ((double)B * H * (W - 1)) + smy / ((double)B * (H - 1) * W);
+        a.loss[0] = (float)(ph + (double)a.smooth_w * smooth);
+        a.loss[1] = (float)ph;
+        a.loss[2] = (float)smooth;
+        a.loss[3] = 0.f;
+        a.ws->counter_fwd = 0;
+        __threadfence();
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_f1_forward(const F1Args& a, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(f1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(FwdSmem));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, a.B);
+    f1_fwd_kernel<<<grid, NT, sizeof(FwdSmem), stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace mvf
