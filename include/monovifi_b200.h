@@ -87,6 +87,39 @@ int mvf_f1_forward_host(const mvf_f1_params* p, const float* disp, const float* 
                         const float* src1, const float* inv_K, const float* P0, const float* P1,
                         const float* noise, const float* mask_rec, float* loss, uint8_t* idx);
 
+/* ---- stand-alone ops behind the reference's layers.py API (autograd pairs) --------------------------------
+ * scratch for the reductions is the same zeroed workspace as F1's (mvf_f1_workspace_bytes(B)). */
+
+/* disp_to_depth, layers.py:16-25.  scaled_disp / depth may be NULL. */
+int mvf_disp_to_depth_fwd(const float* disp, float* scaled_disp, float* depth, size_t n, float min_disp,
+                          float disp_range, void* stream);
+int mvf_disp_to_depth_bwd(const float* disp, const float* g_scaled_disp, const float* g_depth, float* g_disp, size_t n,
+                          float min_disp, float disp_range, void* stream);
+/* BackprojectDepth.forward, layers.py:192-197: depth[B,1,H,W], inv_K[B,4,4] -> cam_points[B,4,H*W] */
+int mvf_backproject_fwd(const float* depth, const float* inv_K, float* cam_points, int B, int H, int W, void* stream);
+int mvf_backproject_bwd(const float* g_cam_points, const float* inv_K, float* g_depth, int B, int H, int W, void* stream);
+/* Project3D.forward, layers.py:214-222 with P = (K@T)[:, :3] ([B,3,4], layers.py:212 stays a torch matmul):
+ * points[B,4,H*W] -> pix_coords[B,H,W,2] in [-1,1] */
+int mvf_project_fwd(const float* points, const float* P, float* pix_coords, int B, int H, int W, float eps, void* stream);
+int mvf_project_bwd(const float* points, const float* P, const float* g_pix_coords, float* g_points, float* g_P,
+                    void* workspace, size_t workspace_bytes, int B, int H, int W, float eps, void* stream);
+/* SSIM.forward, layers.py:277-290 on N = B*C planes.  bwd gives the gradient w.r.t. x (call it with x and y
+ * swapped for y: the formula is symmetric); coef_scratch: 3*N*H*W floats. */
+int mvf_ssim_fwd(const float* x, const float* y, float* out, int N, int H, int W, void* stream);
+int mvf_ssim_bwd(const float* x, const float* y, const float* g_out, float* g_x, float* coef_scratch, int N, int H,
+                 int W, void* stream);
+/* get_smooth_loss, layers.py:231-242: disp[B,1,H,W], img[B,3,H,W] -> loss[1]; gradient w.r.t. disp */
+int mvf_smooth_loss_fwd(const float* disp, const float* img, float* loss, void* workspace, size_t workspace_bytes,
+                        int B, int H, int W, void* stream);
+int mvf_smooth_loss_bwd(const float* disp, const float* img, const float* gout, float* g_disp, int B, int H, int W,
+                        void* stream);
+/* Trainer.compute_SI_log_depth_loss, train.py:924-941: pred/target[B,1,H,W] (HW = H*W), mask or NULL ->
+ * loss[1], stats[B,2] (saved for bwd); bwd gives gradients w.r.t. pred and target (either may be NULL) */
+int mvf_si_log_fwd(const float* pred, const float* target, const float* mask, float* loss, float* stats,
+                   void* workspace, size_t workspace_bytes, int B, size_t HW, float beta, void* stream);
+int mvf_si_log_bwd(const float* pred, const float* target, const float* mask, const float* stats, const float* gout,
+                   float* g_pred, float* g_target, int B, size_t HW, float beta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

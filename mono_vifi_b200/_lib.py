@@ -25,6 +25,18 @@ SIGNATURES = {
     "mvf_f1_forward": (_i, [_P] + [_vp] * 16 + [_vp, _sz, _vp]),
     "mvf_f1_backward": (_i, [_P] + [_vp] * 14 + [_vp, _sz, _vp]),
     "mvf_f1_forward_host": (_i, [_P] + [_vp] * 11),
+    "mvf_disp_to_depth_fwd": (_i, [_vp, _vp, _vp, _sz, _f, _f, _vp]),
+    "mvf_disp_to_depth_bwd": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _vp]),
+    "mvf_backproject_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mvf_backproject_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mvf_project_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    "mvf_project_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _vp]),
+    "mvf_ssim_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mvf_ssim_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mvf_smooth_loss_fwd": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _vp]),
+    "mvf_smooth_loss_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mvf_si_log_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _sz, _f, _vp]),
+    "mvf_si_log_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _sz, _f, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,48 @@
+"""Convolution entry point of the network stacks.
+
+`Conv2d` keeps nn.Conv2d's parameters / state_dict keys (`weight`, `bias`), so checkpoints of the reference load
+unchanged, and routes the arithmetic through `conv2d()`:
+
+  backend "tcgen05"  hand-written sm_100a implicit-GEMM kernels (mono_vifi_b200/csrc/conv_*.cu) for the shapes
+                     they cover (see `tcgen05_supported`);
+  backend "cudnn"    torch's F.conv2d (cuDNN, a LIBRARY baseline -- what the reference itself runs on).
+
+Select with set_backend() or MVF_CONV_BACKEND.  Shapes the tcgen05 kernels do not cover yet fall through to
+cuDNN and are counted in `stats` so the bench can report how much of the conv work ran on which path.
+"""
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+_backend = os.environ.get("MVF_CONV_BACKEND", "cudnn")
+stats = {"tcgen05": 0, "cudnn": 0}
+
+
+def set_backend(name):
+    global _backend
+    if name not in ("cudnn", "tcgen05"):
+        raise ValueError("unknown conv backend %r" % (name,))
+    _backend = name
+
+
+def get_backend():
+    return _backend
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+    if _backend == "tcgen05":
+        from . import conv_tc
+        if conv_tc.supported(x, weight, stride, padding, dilation, groups):
+            stats["tcgen05"] += 1
+            return conv_tc.conv2d(x, weight, bias, stride, padding)
+    stats["cudnn"] += 1
+    return F.conv2d(x, weight, bias, stride, padding, dilation, groups)
+
+
+class Conv2d(nn.Conv2d):
+    def forward(self, x):
+        if self.padding_mode != "zeros":
+            return super().forward(x)
+        return conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)

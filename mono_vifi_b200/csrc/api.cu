@@ -138,4 +138,72 @@ int mvf_f1_forward_host(const mvf_f1_params* p, const float* disp, const float* 
     return rc;
 }
 
+/* ---- unfused layers.py ops ---------------------------------------------------------------------------- */
+#define MVF_RUN(name, expr)                                                     \
+    do {                                                                        \
+        cudaError_t e__ = (expr);                                               \
+        if (e__ != cudaSuccess) return fail(MVF_ERR_CUDA, name, e__);           \
+        return MVF_OK;                                                          \
+    } while (0)
+
+int mvf_disp_to_depth_fwd(const float* disp, float* scaled_disp, float* depth, size_t n, float min_disp,
+                          float disp_range, void* stream) {
+    if (!disp || n == 0) return fail(MVF_ERR_INVALID, "mvf_disp_to_depth_fwd: bad argument");
+    MVF_RUN("mvf_disp_to_depth_fwd", mvf::disp_to_depth_fwd(disp, scaled_disp, depth, n, min_disp, disp_range, (cudaStream_t)stream));
+}
+int mvf_disp_to_depth_bwd(const float* disp, const float* g_scaled_disp, const float* g_depth, float* g_disp, size_t n,
+                          float min_disp, float disp_range, void* stream) {
+    if (!disp || !g_disp || n == 0) return fail(MVF_ERR_INVALID, "mvf_disp_to_depth_bwd: bad argument");
+    MVF_RUN("mvf_disp_to_depth_bwd", mvf::disp_to_depth_bwd(disp, g_scaled_disp, g_depth, g_disp, n, min_disp, disp_range, (cudaStream_t)stream));
+}
+int mvf_backproject_fwd(const float* depth, const float* inv_K, float* cam_points, int B, int H, int W, void* stream) {
+    if (!depth || !inv_K || !cam_points || B <= 0 || H <= 0 || W <= 0) return fail(MVF_ERR_INVALID, "mvf_backproject_fwd: bad argument");
+    MVF_RUN("mvf_backproject_fwd", mvf::backproject_fwd(depth, inv_K, cam_points, B, H, W, (cudaStream_t)stream));
+}
+int mvf_backproject_bwd(const float* g_cam_points, const float* inv_K, float* g_depth, int B, int H, int W, void* stream) {
+    if (!g_cam_points || !inv_K || !g_depth || B <= 0 || H <= 0 || W <= 0) return fail(MVF_ERR_INVALID, "mvf_backproject_bwd: bad argument");
+    MVF_RUN("mvf_backproject_bwd", mvf::backproject_bwd(g_cam_points, inv_K, g_depth, B, H, W, (cudaStream_t)stream));
+}
+int mvf_project_fwd(const float* points, const float* P, float* pix_coords, int B, int H, int W, float eps, void* stream) {
+    if (!points || !P || !pix_coords || B <= 0 || H < 2 || W < 2) return fail(MVF_ERR_INVALID, "mvf_project_fwd: bad argument");
+    MVF_RUN("mvf_project_fwd", mvf::project_fwd(points, P, pix_coords, B, H, W, eps, (cudaStream_t)stream));
+}
+int mvf_project_bwd(const float* points, const float* P, const float* g_pix_coords, float* g_points, float* g_P,
+                    void* workspace, size_t workspace_bytes, int B, int H, int W, float eps, void* stream) {
+    if (!points || !P || !g_pix_coords || !g_points || !g_P || B <= 0) return fail(MVF_ERR_INVALID, "mvf_project_bwd: bad argument");
+    if (!workspace || workspace_bytes < mvf::f1_workspace_bytes(B)) return fail(MVF_ERR_WORKSPACE, "mvf_project_bwd: workspace too small");
+    MVF_RUN("mvf_project_bwd", mvf::project_bwd(points, P, g_pix_coords, g_points, g_P, mvf::ws_fwd_acc((mvf::F1Workspace*)workspace), B, H, W, eps, (cudaStream_t)stream));
+}
+int mvf_ssim_fwd(const float* x, const float* y, float* out, int N, int H, int W, void* stream) {
+    if (!x || !y || !out || N <= 0 || H < 2 || W < 2) return fail(MVF_ERR_INVALID, "mvf_ssim_fwd: bad argument");
+    MVF_RUN("mvf_ssim_fwd", mvf::ssim_fwd(x, y, out, N, H, W, (cudaStream_t)stream));
+}
+int mvf_ssim_bwd(const float* x, const float* y, const float* g_out, float* g_x, float* coef_scratch, int N, int H,
+                 int W, void* stream) {
+    if (!x || !y || !g_out || !g_x || !coef_scratch || N <= 0 || H < 2 || W < 2) return fail(MVF_ERR_INVALID, "mvf_ssim_bwd: bad argument");
+    MVF_RUN("mvf_ssim_bwd", mvf::ssim_bwd(x, y, g_out, g_x, coef_scratch, N, H, W, (cudaStream_t)stream));
+}
+int mvf_smooth_loss_fwd(const float* disp, const float* img, float* loss, void* workspace, size_t workspace_bytes,
+                        int B, int H, int W, void* stream) {
+    if (!disp || !img || !loss || B <= 0 || H < 2 || W < 2) return fail(MVF_ERR_INVALID, "mvf_smooth_loss_fwd: bad argument");
+    if (!workspace || workspace_bytes < mvf::f1_workspace_bytes(B)) return fail(MVF_ERR_WORKSPACE, "mvf_smooth_loss_fwd: workspace too small");
+    MVF_RUN("mvf_smooth_loss_fwd", mvf::smooth_fwd(disp, img, loss, mvf::ws_fwd_acc((mvf::F1Workspace*)workspace), B, H, W, (cudaStream_t)stream));
+}
+int mvf_smooth_loss_bwd(const float* disp, const float* img, const float* gout, float* g_disp, int B, int H, int W,
+                        void* stream) {
+    if (!disp || !img || !g_disp || B <= 0 || H < 2 || W < 2) return fail(MVF_ERR_INVALID, "mvf_smooth_loss_bwd: bad argument");
+    MVF_RUN("mvf_smooth_loss_bwd", mvf::smooth_bwd(disp, img, gout, g_disp, B, H, W, (cudaStream_t)stream));
+}
+int mvf_si_log_fwd(const float* pred, const float* target, const float* mask, float* loss, float* stats,
+                   void* workspace, size_t workspace_bytes, int B, size_t HW, float beta, void* stream) {
+    if (!pred || !target || !loss || !stats || B <= 0 || HW == 0) return fail(MVF_ERR_INVALID, "mvf_si_log_fwd: bad argument");
+    if (!workspace || workspace_bytes < mvf::f1_workspace_bytes(B)) return fail(MVF_ERR_WORKSPACE, "mvf_si_log_fwd: workspace too small");
+    MVF_RUN("mvf_si_log_fwd", mvf::si_log_fwd(pred, target, mask, loss, stats, mvf::ws_fwd_acc((mvf::F1Workspace*)workspace), B, HW, beta, (cudaStream_t)stream));
+}
+int mvf_si_log_bwd(const float* pred, const float* target, const float* mask, const float* stats, const float* gout,
+                   float* g_pred, float* g_target, int B, size_t HW, float beta, void* stream) {
+    if (!pred || !target || !stats || B <= 0 || HW == 0) return fail(MVF_ERR_INVALID, "mvf_si_log_bwd: bad argument");
+    MVF_RUN("mvf_si_log_bwd", mvf::si_log_bwd(pred, target, mask, stats, gout, g_pred, g_target, B, HW, beta, (cudaStream_t)stream));
+}
+
 }  // extern "C"

@@ -24,6 +24,28 @@ constexpr int R2 = 6;                    // window rows per thread in phase 2 (H
 constexpr int NCP = W1 / 2;              // 17 column pairs in phase 2
 constexpr int NITEM2 = 3 * NCP * (H1 / R2);
 
+// Geometry of the recompute.  Exact (IEEE divisions, bit-identical sampling weights to the forward) by
+// default; -DMVF_BWD_FAST_GEOMETRY=1 switches to MUFU reciprocals (coordinates differ by ~1e-4 px).
+#ifndef MVF_BWD_FAST_GEOMETRY
+#define MVF_BWD_FAST_GEOMETRY 0
+#endif
+__device__ __forceinline__ void project_bwd_tap(float depth, const float c[3], const float* __restrict__ P, const Geo& g,
+                                                Tap& t, float X[3], float pr[3], float& rz) {
+#if MVF_BWD_FAST_GEOMETRY
+    project_tap_fast(depth, c, P, g, t, X, pr, rz);
+#else
+    project_tap(depth, c, P, g, t, X, pr);
+    rz = __fdividef(1.0f, pr[2] + 1e-7f);
+#endif
+}
+__device__ __forceinline__ float depth_bwd(float d, float min_disp, float range) {
+#if MVF_BWD_FAST_GEOMETRY
+    return __fdividef(1.0f, min_disp + range * d);
+#else
+    return disp_to_depth(d, min_disp, range);
+#endif
+}
+
 struct __align__(16) BwdSmem {
     float2 T2[3][H2][W2];     // target {t,t}
     float2 Wp[3][H2][W2];     // warped {warp0, warp1}
@@ -136,14 +158,14 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
             float tv[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) tv[c] = __ldg(tgtb + c * HW + i);
-            float depth = __fdividef(1.0f, a.min_disp + a.disp_range * d);
+            float depth = depth_bwd(d, a.min_disp, a.disp_range);
             float cr[3], X[3], pr[3], rz;
             cam_ray(sm.cst, (float)x, (float)y, cr);
             Tap t0, t1;
             float w0[3], w1[3], dx0[3], dy0[3], dx1[3], dy1[3];
-            project_tap_fast(depth, cr, sm.cst + 12, g, t0, X, pr, rz);
+            project_bwd_tap(depth, cr, sm.cst + 12, g, t0, X, pr, rz);
             bilinear3_grad(s0b, H, W, t0, w0, dx0, dy0);
-            project_tap_fast(depth, cr, sm.cst + 24, g, t1, X, pr, rz);
+            project_bwd_tap(depth, cr, sm.cst + 24, g, t1, X, pr, rz);
             bilinear3_grad(s1b, H, W, t1, w1, dx1, dy1);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -253,8 +275,7 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
             const int col = 2 * cp + j, x = tx0 + col;
             if (y >= H || x >= W) continue;
             const float d = sm.D[row + 1][col + 1];
-            const float sdv = a.min_disp + a.disp_range * d;
-            const float depth = __fdividef(1.0f, sdv);
+            const float depth = depth_bwd(d, a.min_disp, a.disp_range);
             float cr[3];
             cam_ray(sm.cst, (float)x, (float)y, cr);
             float gdepth = 0.f;
@@ -263,7 +284,7 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
                 const float* P = sm.cst + 12 + 12 * k;
                 Tap t;
                 float X[3], pr[3], rz;
-                project_tap_fast(depth, cr, P, g, t, X, pr, rz);
+                project_bwd_tap(depth, cr, P, g, t, X, pr, rz);
                 float gx = k == 0 ? gix[j].x : gix[j].y, gy = k == 0 ? giy[j].x : giy[j].y;
                 if (!(t.ixr > 0.0f && t.ixr < g.wm1)) gx = 0.f;
                 if (!(t.iyr > 0.0f && t.iyr < g.hm1)) gy = 0.f;
