@@ -144,6 +144,9 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
     const float* tgtb = a.tgt + (size_t)b * 3 * HW;
     const float* s0b = a.src0 + (size_t)b * 3 * HW;
     const float* s1b = a.src1 + (size_t)b * 3 * HW;
+    const uint8_t* __restrict__ idxb = a.idx + (size_t)b * HW;
+    const float* __restrict__ mkb = a.mask ? a.mask + (size_t)b * HW : nullptr;
+    const int HWi = H * W;
 
     // ---------------- phase 1 ---------------------------------------------------------------------------------
     {
@@ -153,20 +156,20 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
             int hy = p / W2, hx = p - hy * W2;
             int ry = ty0 - 2 + hy, rx = tx0 - 2 + hx;
             int y = clampi(reflect1(ry, H), 0, H - 1), x = clampi(reflect1(rx, W), 0, W - 1);
-            size_t i = (size_t)y * W + x;
+            const int i = y * W + x;
             float d = __ldg(dispb + i);
             float tv[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) tv[c] = __ldg(tgtb + c * HW + i);
+            for (int c = 0; c < 3; ++c) tv[c] = __ldg(tgtb + (i + c * HWi));
             float depth = depth_bwd(d, a.min_disp, a.disp_range);
             float cr[3], X[3], pr[3], rz;
             cam_ray(sm.cst, (float)x, (float)y, cr);
             Tap t0, t1;
             float w0[3], w1[3], dx0[3], dy0[3], dx1[3], dy1[3];
             project_bwd_tap(depth, cr, sm.cst + 12, g, t0, X, pr, rz);
-            bilinear3_grad(s0b, H, W, t0, w0, dx0, dy0);
+            gather3_grad(s0b, HWi, W, corner_of(t0, H, W), w0, dx0, dy0);
             project_bwd_tap(depth, cr, sm.cst + 24, g, t1, X, pr, rz);
-            bilinear3_grad(s1b, H, W, t1, w1, dx1, dy1);
+            gather3_grad(s1b, HWi, W, corner_of(t1, H, W), w1, dx1, dy1);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 sm.T2[c][hy][hx] = make_float2(tv[c], tv[c]);
@@ -177,8 +180,8 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
                 const bool inimg = (ry == y) && (rx == x) && ry >= 0 && rx >= 0;  // raw position is a real pixel
                 float2 gs = make_float2(0.f, 0.f);
                 if (inimg) {
-                    int sel = a.idx[(size_t)b * HW + i];
-                    float m = a.mask ? __ldg(a.mask + (size_t)b * HW + i) : 1.0f;
+                    int sel = idxb[i];
+                    float m = mkb ? __ldg(mkb + i) : 1.0f;
                     float sh0, sh1;
                     if (avg) sh0 = sh1 = (!am || sel == first_rep) ? 0.5f : 0.0f;
                     else { sh0 = (sel == first_rep) ? 1.0f : 0.0f; sh1 = (sel == first_rep + 1) ? 1.0f : 0.0f; }
@@ -214,6 +217,7 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
     __syncthreads();
 
     // ---------------- phase 3: adjoint stencil, chain rule to disp and P ---------------------------------------
+    float* __restrict__ gdb = a.g_disp + (size_t)b * HW;
     float gP[24];
 #pragma unroll
     for (int q = 0; q < 24; ++q) gP[q] = 0.f;
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
                 gnd -= cyn * sgnf(sm.D[row][col + 1] - d) * __expf(-(gi / 3.0f));
             }
             gd += gnd / den - shift;
-            a.g_disp[(size_t)b * HW + (size_t)y * W + x] = gd;
+            gdb[y * W + x] = gd;
         }
     }
     // ---------------- block reduction of grad_P (scratch aliases CF), fixed-point atomics ---------------------

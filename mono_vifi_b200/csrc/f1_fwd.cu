@@ -116,7 +116,7 @@ __device__ __forceinline__ void emit(FwdSmem& sm, int c, int orow, int cx, const
     }
 }
 
-__global__ void __launch_bounds__(NT, 2) f1_fwd_kernel(const F1Args a) {
+__global__ void __maxnreg__(112) f1_fwd_kernel(const F1Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -130,34 +130,36 @@ __global__ void __launch_bounds__(NT, 2) f1_fwd_kernel(const F1Args a) {
     __syncthreads();
 
     // ---------------- phase 1: view synthesis at tile + halo, stage everything in shared memory -------------
+    // (all per-image offsets are 32-bit: the API rejects tensors with 2^31 or more elements)
     {
         const Geo g = make_geo(H, W);
-        const float* dispb = a.disp + (size_t)b * HW;
-        const float* tgtb = a.tgt + (size_t)b * 3 * HW;
-        const float* s0b = a.src0 + (size_t)b * 3 * HW;
-        const float* s1b = a.src1 + (size_t)b * 3 * HW;
+        const int HWi = H * W;
+        const float* __restrict__ dispb = a.disp + (size_t)b * HW;
+        const float* __restrict__ tgtb = a.tgt + (size_t)b * 3 * HW;
+        const float* __restrict__ s0b = a.src0 + (size_t)b * 3 * HW;
+        const float* __restrict__ s1b = a.src1 + (size_t)b * 3 * HW;
         for (int p = tid; p < HHT * HWD; p += NT) {
-            int hy = p / HWD, hx = p - hy * HWD;
-            int ry = ty0 - 1 + hy, rx = tx0 - 1 + hx;          // raw (possibly padded / out-of-image) coords
-            int y = clampi(reflect1(ry, H), 0, H - 1), x = clampi(reflect1(rx, W), 0, W - 1);
-            size_t i = (size_t)y * W + x;
-            float d = __ldg(dispb + i);
+            const int hy = p / HWD, hx = p - hy * HWD;
+            const int ry = ty0 - 1 + hy, rx = tx0 - 1 + hx;    // raw (possibly padded / out-of-image) coords
+            const int y = clampi(reflect1(ry, H), 0, H - 1), x = clampi(reflect1(rx, W), 0, W - 1);
+            const int i = y * W + x;
+            const float d = __ldg(dispb + i);
             float tv[3], sv0[3], sv1[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                tv[c] = __ldg(tgtb + c * HW + i);
-                sv0[c] = __ldg(s0b + c * HW + i);
-                sv1[c] = __ldg(s1b + c * HW + i);
+                tv[c] = __ldg(tgtb + (i + c * HWi));
+                sv0[c] = __ldg(s0b + (i + c * HWi));
+                sv1[c] = __ldg(s1b + (i + c * HWi));
             }
-            float depth = disp_to_depth(d, a.min_disp, a.disp_range);
+            const float depth = disp_to_depth(d, a.min_disp, a.disp_range);
             float cr[3], X[3], pr[3];
             cam_ray(sm.cst, (float)x, (float)y, cr);
             Tap t0, t1;
             project_tap(depth, cr, sm.cst + 12, g, t0, X, pr);
             project_tap(depth, cr, sm.cst + 24, g, t1, X, pr);
             float w0[3], w1[3];
-            bilinear3(s0b, H, W, t0, w0);
-            bilinear3(s1b, H, W, t1, w1);
+            gather3(s0b, HWi, W, corner_of(t0, H, W), w0);
+            gather3(s1b, HWi, W, corner_of(t1, H, W), w1);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 sm.T2[c][hy][hx] = make_float2(tv[c], tv[c]);
@@ -207,38 +209,45 @@ __global__ void __launch_bounds__(NT, 2) f1_fwd_kernel(const F1Args a) {
     {
         const bool avg = (a.flags & F_AVG_REPROJECTION) != 0, am = !(a.flags & F_DISABLE_AUTOMASKING);
         const int nid = am ? (avg ? 1 : 2) : 0;
+        const int HWi = H * W;
+        const float* __restrict__ nzb = (a.noise && nid) ? a.noise + (size_t)b * nid * HW : nullptr;
+        const float* __restrict__ mkb = a.mask ? a.mask + (size_t)b * HW : nullptr;
+        uint8_t* __restrict__ idxb = a.idx + (size_t)b * HW;
+        float* __restrict__ tob = a.to_opt ? a.to_opt + (size_t)b * HW : nullptr;
         for (int p = tid; p < TW * TH; p += NT) {
-            int row = p / TW, col = p - row * TW;
-            int y = ty0 + row, x = tx0 + col;
+            const int row = p / TW, col = p - row * TW;
+            const int y = ty0 + row, x = tx0 + col;
             if (y >= H || x >= W) continue;
-            size_t i = (size_t)y * W + x;
-            float4 r0 = sm.REP[0][row][col], r1 = sm.REP[1][row][col], r2 = sm.REP[2][row][col];
-            float id0 = r0.x + r1.x + r2.x, id1 = r0.y + r1.y + r2.y;
-            float w0 = r0.z + r1.z + r2.z, w1 = r0.w + r1.w + r2.w;
-            float comb[4];
-            int nc = 0;
-            if (am) {
-                const float* nz = a.noise ? a.noise + (size_t)b * nid * HW + i : nullptr;
-                if (avg) {
-                    comb[nc++] = (id0 + id1) * 0.5f + (nz ? __ldg(nz) * 0.00001f : 0.f);
+            const int i = y * W + x;
+            const float4 r0 = sm.REP[0][row][col], r1 = sm.REP[1][row][col], r2 = sm.REP[2][row][col];
+            const float id0 = r0.x + r1.x + r2.x, id1 = r0.y + r1.y + r2.y;
+            const float w0 = r0.z + r1.z + r2.z, w1 = r0.w + r1.w + r2.w;
+            // combined = cat(identity (+1e-5 noise), reprojection) ; min / argmin, first minimum wins (train.py:1023-1033)
+            float m;
+            int best = 0;
+            if (!avg) {
+                if (am) {
+                    m = id0 + (nzb ? __ldg(nzb + i) * 0.00001f : 0.f);
+                    const float c1 = id1 + (nzb ? __ldg(nzb + (i + HWi)) * 0.00001f : 0.f);
+                    if (c1 < m) { m = c1; best = 1; }
+                    if (w0 < m) { m = w0; best = 2; }
+                    if (w1 < m) { m = w1; best = 3; }
                 } else {
-                    comb[nc++] = id0 + (nz ? __ldg(nz) * 0.00001f : 0.f);
-                    comb[nc++] = id1 + (nz ? __ldg(nz + HW) * 0.00001f : 0.f);
+                    m = w0;
+                    if (w1 < m) { m = w1; best = 1; }
+                }
+            } else {
+                const float wa = (w0 + w1) * 0.5f;
+                if (am) {
+                    m = (id0 + id1) * 0.5f + (nzb ? __ldg(nzb + i) * 0.00001f : 0.f);
+                    if (wa < m) { m = wa; best = 1; }
+                } else {
+                    m = wa;
                 }
             }
-            if (avg) {
-                comb[nc++] = (w0 + w1) * 0.5f;
-            } else {
-                comb[nc++] = w0;
-                comb[nc++] = w1;
-            }
-            int best = 0;
-            float m = comb[0];
-            for (int q = 1; q < nc; ++q)
-                if (comb[q] < m) { m = comb[q]; best = q; }
-            if (a.mask) m *= __ldg(a.mask + (size_t)b * HW + i);
-            a.idx[(size_t)b * HW + i] = (uint8_t)best;
-            if (a.to_opt) a.to_opt[(size_t)b * HW + i] = m;
+            if (mkb) m *= __ldg(mkb + i);
+            idxb[i] = (uint8_t)best;
+            if (tob) tob[i] = m;
             photo += m;
             // edge-aware smoothness on the raw disparity; the 1/(mean+eps) factor is applied per image later
             float d = sm.D[row][col];

@@ -176,6 +176,17 @@ class BackprojectDepth(nn.Module):
         return _Backproject.apply(depth, inv_K, self.batch_size, self.height, self.width)
 
 
+def matmul_KT(K, T):
+    """`torch.matmul(K, T)` of layers.py:212 for [B,4,4] operands, written as separately rounded multiply / add
+    steps in k order.  That is what torch's CPU bmm produces for this shape (no FMA, verified bit for bit against
+    the golden vectors in tests/test_networks_api.py), and -- unlike cuBLAS -- it gives the same bits on the GPU, so
+    the sampling grid downstream is bit-identical to the CPU reference's.  Differentiable (plain torch ops)."""
+    P = K[:, :, 0:1] * T[:, 0:1, :]
+    for j in range(1, 4):
+        P = P + K[:, :, j:j + 1] * T[:, j:j + 1, :]
+    return P
+
+
 class _Project(torch.autograd.Function):
     @staticmethod
     def forward(ctx, points, P, B, H, W, eps):
@@ -200,7 +211,7 @@ class _Project(torch.autograd.Function):
 
 
 class Project3D(nn.Module):
-    """layers.py:200-222.  `K @ T` (layers.py:212) stays a torch matmul so its bits match the reference's
+    """layers.py:200-222.  `K @ T` (layers.py:212) goes through matmul_KT so its bits match the reference's
     (exactness recipe); the [3,4] x [4,HW] product, divide and normalise run in one kernel."""
 
     def __init__(self, batch_size, height, width, eps=1e-7):
@@ -208,7 +219,7 @@ class Project3D(nn.Module):
         self.batch_size, self.height, self.width, self.eps = batch_size, height, width, eps
 
     def forward(self, points, K, T):
-        P = torch.matmul(K, T)[:, :3, :]
+        P = matmul_KT(K, T)[:, :3, :]
         return _Project.apply(points, P, self.batch_size, self.height, self.width, float(self.eps))
 
 

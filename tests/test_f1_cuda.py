@@ -110,8 +110,10 @@ def test_backward_vs_oracle(name):
         gp4 = np.concatenate([gP.cpu().numpy(), np.zeros((B, 1, 4), np.float32)], 1)
         gT = np.einsum("bji,bjk->bik", c["K"].astype(np.float64), gp4.astype(np.float64))
         ref = g["grad_T"][k]
-        s = np.abs(ref).max() + 1e-12
-        assert np.abs(gT - ref).max() <= 3e-3 * s, (k, np.abs(gT - ref).max(), s)
+        # K^T mixes rows of grad_P with weights ~(W, H, 1) and the terms cancel, so the error bound of an entry is
+        # the relative accuracy of grad_P (2e-3, asserted above) times |K|^T |grad_P|, not times |grad_T|
+        bound = 2e-3 * np.einsum("bji,bjk->bik", np.abs(c["K"]).astype(np.float64), np.abs(gp4).astype(np.float64)).max()
+        assert np.abs(gT - ref).max() <= bound, (k, np.abs(gT - ref).max(), bound)
 
 
 @pytest.mark.parametrize("shape", [(1, 3, 3), (1, 5, 7), (3, 17, 33), (2, 32, 64), (1, 48, 100), (2, 96, 320)])

@@ -60,6 +60,8 @@ def test_transformation_from_parameters_matches_golden():
         T = L.transformation_from_parameters(torch.from_numpy(c["axisangle"][k]), torch.from_numpy(c["translation"][k]),
                                              invert=(k == 1))
         assert np.array_equal(T.numpy(), g["T"][k])   # same op sequence -> same bits
+        P = L.matmul_KT(torch.from_numpy(c["K"]), T)[:, :3]
+        assert np.array_equal(P.numpy(), g["P"][k])   # layers.py:212 (K @ T), the reference's bits
 
 
 def test_library_exports_every_declared_symbol():
