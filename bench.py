@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Headline benchmark: training images/sec of the Mono-ViFI self-supervised inner loop (ResNet18 depth + pose,
+192x640, batch 12 per GPU, synthetic 3-frame triplets), plus achieved HBM GB/s of the fused warp+SSIM kernel.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N ...            the reference path on the host CPU cores (rank 0 only)
+
+One JSON line on stdout (rank 0).  A "step" = zero_grad -> forward (2 pose nets, depth encoder + decoder, fused
+view synthesis + photometric loss) -> backward -> gradient all-reduce (N>1) -> clip -> AdamW, i.e. the single-frame
+slice of train.py:656-666 / 728-750 that BASELINE.json configs[1] names.
+  value : device-timed, inputs resident in HBM          e2e : same step fed from pinned host memory each step
+                                                              (H2D inside the timed region, loss read back)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "training images/sec at 192x640 ResNet18, 1/2/4/8 B200; warp+SSIM HBM GB/s"
+UNIT = "images/s"
+WORKLOAD = "ResNet18 single-frame 192x640 batch 12 per GPU (BASELINE configs[1]): 2 pose nets + depth enc/dec + fused warp/SSIM loss group, fwd+bwd+AdamW"
+F1_FWD_BYTES_PER_PX = 40.0 + 8.0   # disp 4 + tgt 12 + 2 x src 12 (+ tie-break noise 8)  SURVEY.md 8(d)
+F1_BWD_BYTES_PER_PX = 44.0         # re-read 40, write grad_disp 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=12, help="per-GPU batch (configs[1]: 12)")
+    ap.add_argument("--height", type=int, default=192)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--cpu-batch", type=int, default=2, help="bounded CPU sample: images per CPU step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--conv-backend", default=os.environ.get("MVF_CONV_BACKEND", "cudnn"))
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's path on host cores.  The reference is Python over torch and is not present on the GPU
+# box, so this is the PORT: the same networks as plain torch modules on CPU (ATen convolutions, all host threads)
+# and the C oracle (oracle/f1_oracle.c) for view synthesis + photometric loss, one thread per sample.
+# ------------------------------------------------------------------------------------------------------------
+def _cpu_step_factory(B, H, W):
+    import numpy as np
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import f1_oracle as O
+    from mono_vifi_b200 import layers as L, trainer as TR
+
+    pool = ThreadPoolExecutor(max_workers=B)
+
+    class OracleLoss(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, disp, P0, P1, tgt, s0, s1, inv_K, noise):
+            a = [t.detach().numpy() for t in (disp, tgt, s0, s1, inv_K, P0, P1, noise)]
+
+            def one(b):
+                sl = [x[b:b + 1] for x in a]
+                return O.f1_forward(sl[0], sl[1], sl[2], sl[3], sl[4], sl[5], sl[6], sl[7], None, full=False)
+            outs = list(pool.map(one, range(B)))
+            ctx.a, ctx.idx = a, [o["idx"] for o in outs]
+            return torch.tensor(float(np.mean([o["loss"][0] for o in outs])), dtype=torch.float32)
+
+        @staticmethod
+        def backward(ctx, g):
+            a, go = ctx.a, float(g) / B
+
+            def one(b):
+                sl = [x[b:b + 1] for x in a]
+                return O.f1_backward(sl[0], sl[1], sl[2], sl[3], sl[4], sl[5], sl[6], ctx.idx[b], None, go)
+            outs = list(pool.map(one, range(B)))
+            gd = torch.from_numpy(np.concatenate([o[0] for o in outs], 0))
+            gP0 = torch.from_numpy(np.concatenate([o[1] for o in outs], 0))
+            gP1 = torch.from_numpy(np.concatenate([o[2] for o in outs], 0))
+            return gd, gP0, gP1, None, None, None, None, None
+
+    opt = TR.Options(batch_size=B, height=H, width=W)
+    torch.manual_seed(1234)
+    models = TR.build_models(opt, torch.device("cpu"))
+    for m in models.values():
+        m.train()
+    params = [p for m in models.values() for p in m.parameters()]
+    optim = torch.optim.AdamW(params, lr=opt.learning_rate, weight_decay=opt.weight_decay)
+    inputs = TR.synthetic_inputs(opt)
+
+    def step():
+        optim.zero_grad(set_to_none=True)
+        K, inv_K = inputs[("K", 0)], inputs[("inv_K", 0)]
+        _, pose_0_n1 = TR.predict_poses(models, inputs[("color_aug", -1, 0)], inputs[("color_aug", 0, 0)])
+        pose_0_p1, _ = TR.predict_poses(models, inputs[("color_aug", 0, 0)], inputs[("color_aug", 1, 0)])
+        disp = models["depth"](models["encoder"](inputs[("color_aug", 0, 0)]))[("disp", 0)]
+        P0, P1 = L.matmul_KT(K, pose_0_n1)[:, :3], L.matmul_KT(K, pose_0_p1)[:, :3]
+        noise = torch.randn(B, 2, H, W)
+        loss = OracleLoss.apply(disp, P0, P1, inputs[("color", 0, 0)], inputs[("color", -1, 0)],
+                                inputs[("color", 1, 0)], inv_K, noise)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], opt.clip_grad)
+        optim.step()
+        return float(loss)
+    return step
+
+
+def time_cpu(B, H, W, steps, warmup, budget_s=25.0):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = _cpu_step_factory(B, H, W)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < steps:
+        step()
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": B * n / dt, "ms_per_step": 1e3 * dt / n, "steps": n, "cores": cores,
+            "sample": "%d steps of batch %d at %dx%d (same step, bounded batch)" % (n, B, H, W)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = time_cpu(args.cpu_batch, args.height, args.width, args.steps, max(1, min(args.warmup, 2)), budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": max(1, min(args.warmup, 2)), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "height": args.height, "width": args.width,
+                       "note": "reference path on host CPU cores: ATen convolutions (all threads) + C oracle of the "
+                               "view-synthesis/photometric loss, bounded sample of batch %d per step" % args.cpu_batch},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mono_vifi_b200 import _lib, conv, ddp, fused, trainer as TR
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device: there is no CPU fallback")
+    _lib.lib()  # fail loudly if the CUDA extension is missing
+    rank, local, world = ddp.init_from_env("nccl")
+    if world != args.gpus and rank == 0:
+        sys.stderr.write("warning: --gpus %d but WORLD_SIZE %d\n" % (args.gpus, world))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    conv.set_backend(args.conv_backend)
+    opt = TR.Options(batch_size=args.batch, height=args.height, width=args.width)
+    torch.manual_seed(1234)
+    step = TR.TrainStep(opt, dev, distributed=(world > 1))
+    step.train()
+    ddp.broadcast_parameters(step.params)
+    # two distinct synthetic batches per rank, rotated, in pinned host memory and (for `value`) resident in HBM
+    host = [TR.synthetic_inputs(opt, seed=1234 + 17 * rank + s, pin=True) for s in range(2)]
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(resident[i % 2])
+    # ---- timed region 1: device-resident inputs ---------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    fused.timing = []
+    l0 = dict(fused.launches)
+    barrier()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(resident[i % 2])
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1) / args.steps
+    kt = {"f1_fwd": [], "f1_bwd": []}
+    for tag, a, b in fused.timing:
+        kt[tag].append(a.elapsed_time(b))
+    fused.timing = None
+    my_launches = sum(fused.launches[k] - l0[k] for k in l0) + 0
+    # ---- timed region 2: end to end from pinned host memory -----------------------------------------------------
+    stage = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    last = 0.0
+    for i in range(args.steps):
+        buf = stage[i % 2]
+        for k, v in host[i % 2].items():
+            buf[k].copy_(v, non_blocking=True)
+        last = float(step(buf))  # D2H read of the step's loss
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3) / args.steps
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return 0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    px = args.batch * args.height * args.width
+
+    def roof(tag, bpp):
+        v = sorted(kt[tag])
+        if not v:
+            return None
+        avg_ms = sum(v) / len(v)
+        ach = bpp * px / (avg_ms * 1e-3) / 1e9
+        return {"kernel": tag + "_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                "traffic": None, "avg_launch_us": avg_ms * 1e3, "launches_timed": len(v), "bytes_per_px": bpp,
+                "peak_source": peak_src}
+    line = {"metric": METRIC, "value": args.batch * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (tf32 tensor-core convolutions, as torch's cuDNN default)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": args.batch, "global_batch": args.batch * world,
+                       "height": args.height, "width": args.width, "parallelism": "dp%d" % world,
+                       "conv_backend": conv.get_backend(), "conv_calls": dict(conv.stats),
+                       "l2": "working set (activations, several GB) is far larger than the 126 MB L2; inputs rotate between two batches"},
+            "e2e": {"value": args.batch * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": my_launches, "clocks": clocks, "loss": last,
+            "roofline": roof("f1_fwd", F1_FWD_BYTES_PER_PX), "roofline_bwd": roof("f1_bwd", F1_BWD_BYTES_PER_PX)}
+    if world == 1 and not args.no_cpu_baseline:
+        r = time_cpu(args.cpu_batch, args.height, args.width, 3, 1, budget_s=25.0)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    rc = run_ours(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+    return rc
+
+
+if __name__ == "__main__":
+    sys.exit(main())

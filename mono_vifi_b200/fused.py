@@ -9,6 +9,23 @@ from . import _lib
 
 _workspaces = {}
 
+# launch accounting for bench.py: number of F1 kernel launches, and -- when `timing` is a list -- a pair of CUDA
+# events around every launch (recorded on the launching stream), tagged "f1_fwd" / "f1_bwd"
+launches = {"f1_fwd": 0, "f1_bwd": 0}
+timing = None
+
+
+def _timed(tag, fn):
+    launches[tag] += 1
+    if timing is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn()
+    e1.record()
+    timing.append((tag, e0, e1))
+    return rc
+
 
 def _ptr(t):
     return None if t is None else t.data_ptr()
@@ -67,9 +84,10 @@ def f1_forward_raw(disp, tgt, src0, src1, inv_K, P0, P1, noise=None, mask_rec=No
         out.update(x0y0=x0y0, warp0=w0, warp1=w1, to_optimise=topt)
     prm = _lib.f1_params(B, H, W, min_depth, max_depth, smooth_w, flags)
     ws, stream = workspace(dev, B)
-    rc = _lib.lib().mvf_f1_forward(prm, _ptr(disp), _ptr(tgt), _ptr(src0), _ptr(src1), _ptr(inv_K), _ptr(P0), _ptr(P1),
-                                   _ptr(noise), _ptr(mask_rec), _ptr(out["loss"]), _ptr(out["stats"]), _ptr(out["idx"]),
-                                   _ptr(x0y0), _ptr(w0), _ptr(w1), _ptr(topt), ws.data_ptr(), ws.numel(), stream)
+    rc = _timed("f1_fwd", lambda: _lib.lib().mvf_f1_forward(
+        prm, _ptr(disp), _ptr(tgt), _ptr(src0), _ptr(src1), _ptr(inv_K), _ptr(P0), _ptr(P1), _ptr(noise), _ptr(mask_rec),
+        _ptr(out["loss"]), _ptr(out["stats"]), _ptr(out["idx"]), _ptr(x0y0), _ptr(w0), _ptr(w1), _ptr(topt),
+        ws.data_ptr(), ws.numel(), stream))
     _lib.check(rc, "mvf_f1_forward")
     out["_saved"] = (disp, tgt, src0, src1, inv_K, P0, P1, mask_rec)
     return out
@@ -85,9 +103,9 @@ def f1_backward_raw(saved, idx, stats, gout=None, min_depth=0.1, max_depth=100.0
         gout = _prep(gout.reshape(1))
     prm = _lib.f1_params(B, H, W, min_depth, max_depth, smooth_w, flags)
     ws, stream = workspace(dev, B)
-    rc = _lib.lib().mvf_f1_backward(prm, _ptr(disp), _ptr(tgt), _ptr(src0), _ptr(src1), _ptr(inv_K), _ptr(P0), _ptr(P1),
-                                    _ptr(mask_rec), _ptr(idx), _ptr(stats), _ptr(gout), _ptr(g_disp), _ptr(g_P0),
-                                    _ptr(g_P1), ws.data_ptr(), ws.numel(), stream)
+    rc = _timed("f1_bwd", lambda: _lib.lib().mvf_f1_backward(
+        prm, _ptr(disp), _ptr(tgt), _ptr(src0), _ptr(src1), _ptr(inv_K), _ptr(P0), _ptr(P1), _ptr(mask_rec), _ptr(idx),
+        _ptr(stats), _ptr(gout), _ptr(g_disp), _ptr(g_P0), _ptr(g_P1), ws.data_ptr(), ws.numel(), stream))
     _lib.check(rc, "mvf_f1_backward")
     return g_disp, g_P0, g_P1
 

@@ -1,0 +1,130 @@
+"""Training-step orchestration of the hot path (host side).
+
+Mirrors the part of the reference's `Trainer` that BASELINE.json's north_star names -- `predict_poses`
+(train.py:943-954), the single-frame loss group of `process_batch` (train.py:728-729, 736, 739, 747-750),
+backward, gradient clipping and AdamW (train.py:659-666) -- on top of the drop-in networks and the fused
+photometric-loss kernel.  Data-parallel training shards the batch across ranks; gradients are averaged with ONE
+NCCL all-reduce over a flat fp32 arena (mono_vifi_b200/ddp.py) instead of the reference's five DDP wrappers.
+"""
+import torch
+
+from . import layers as L
+from . import networks as N
+from .ddp import FlatGradAllReduce
+from .fused import fused_photometric_loss
+
+
+class Options:
+    """The hot-path subset of options.py (defaults: options.py:68-209)."""
+
+    def __init__(self, **kw):
+        self.height, self.width, self.batch_size = 192, 640, 12
+        self.min_depth, self.max_depth = 0.1, 100.0
+        self.disparity_smoothness = 1e-3
+        self.no_ssim = self.avg_reprojection = self.disable_automasking = False
+        self.learning_rate, self.weight_decay, self.clip_grad = 1e-4, 0.01, 5.0
+        self.num_layers = 18
+        self.tie_break_noise = True  # train.py:1023: torch.randn * 1e-5 on the identity terms
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise AttributeError("unknown option %r" % k)
+            setattr(self, k, v)
+
+
+def build_models(opt, device):
+    """train.py:142-190 for backbone ResNet18 (weights_init=scratch)."""
+    models = {}
+    models["encoder"] = N.monodepth2.DepthEncoder(opt.num_layers, False)
+    models["depth"] = N.monodepth2.DepthDecoder(models["encoder"].num_ch_enc, range(1))
+    models["pose_encoder"] = N.posenet.ResnetEncoder(opt.num_layers, False, num_input_images=2)
+    models["pose"] = N.posenet.PoseDecoder(models["pose_encoder"].num_ch_enc, num_input_features=1,
+                                           num_frames_to_predict_for=2)
+    for m in models.values():
+        m.to(device)
+    return models
+
+
+def predict_poses(models, img_0, img_1):
+    """train.py:943-954"""
+    feats = [models["pose_encoder"](torch.cat([img_0, img_1], 1))]
+    axisangle, translation = models["pose"](feats)
+    pose = L.transformation_from_parameters(axisangle[:, 0], translation[:, 0], invert=False)
+    pose_inv = L.transformation_from_parameters(axisangle[:, 0], translation[:, 0], invert=True)
+    return pose, pose_inv
+
+
+def loss_group(opt, disp, img_tgt, T0, T1, img_src0, img_src1, K, inv_K, mask_rec=None, noise=None):
+    """generate_images_pred x2 + compute_losses_base (train.py:747-750) as ONE fused kernel launch."""
+    P0 = L.matmul_KT(K, T0)[:, :3, :]
+    P1 = L.matmul_KT(K, T1)[:, :3, :]
+    if noise is None and opt.tie_break_noise and not opt.disable_automasking:
+        B, _, H, W = disp.shape
+        noise = torch.randn(B, 1 if opt.avg_reprojection else 2, H, W, device=disp.device)
+    return fused_photometric_loss(disp, img_tgt, img_src0, img_src1, inv_K, P0, P1, noise, mask_rec, opt.min_depth,
+                                  opt.max_depth, opt.disparity_smoothness, opt.no_ssim, opt.avg_reprojection,
+                                  opt.disable_automasking)
+
+
+def single_frame_losses(models, inputs, opt):
+    """The single-frame slice of process_batch: train.py:728-729 (poses), 736 + 739 (depth), 747-750 (loss)."""
+    img_n1, img_0, img_p1 = inputs[("color", -1, 0)], inputs[("color", 0, 0)], inputs[("color", 1, 0)]
+    K, inv_K = inputs[("K", 0)], inputs[("inv_K", 0)]
+    pose_n1_0, pose_0_n1 = predict_poses(models, inputs[("color_aug", -1, 0)], inputs[("color_aug", 0, 0)])
+    pose_0_p1, pose_p1_0 = predict_poses(models, inputs[("color_aug", 0, 0)], inputs[("color_aug", 1, 0)])
+    disp_0 = models["depth"](models["encoder"](inputs[("color_aug", 0, 0)]))[("disp", 0)]
+    loss, auto_mask = loss_group(opt, disp_0, img_0, pose_0_n1, pose_0_p1, img_n1, img_p1, K, inv_K)
+    return {"loss": loss, "loss_base": loss, "disp": disp_0, "auto_mask": auto_mask}
+
+
+class TrainStep:
+    """zero_grad -> forward -> backward -> (all-reduce) -> clip -> AdamW  (train.py:656-666)."""
+
+    def __init__(self, opt, device, models=None, distributed=False):
+        self.opt, self.device = opt, device
+        self.models = models if models is not None else build_models(opt, device)
+        # the reference appends every model's parameters (train.py:198-200)
+        self.params = [p for m in self.models.values() for p in m.parameters()]
+        self.optimizer = torch.optim.AdamW(self.params, lr=opt.learning_rate, weight_decay=opt.weight_decay)
+        self.reducer = FlatGradAllReduce(self.params) if distributed else None
+
+    def train(self):
+        for m in self.models.values():
+            m.train()
+
+    def forward_backward(self, inputs):
+        if self.reducer is not None:
+            self.reducer.attach()  # zeroes the flat arena and points every .grad at its slice
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
+        out = single_frame_losses(self.models, inputs, self.opt)
+        out["loss"].backward()
+        if self.reducer is not None:
+            self.reducer.allreduce_mean()
+        return out
+
+    def __call__(self, inputs):
+        out = self.forward_backward(inputs)
+        if self.opt.clip_grad is not None and self.opt.clip_grad > 0:
+            torch.nn.utils.clip_grad_norm_([p for p in self.params if p.grad is not None], self.opt.clip_grad)
+        self.optimizer.step()
+        return out["loss"].detach()
+
+
+def synthetic_inputs(opt, device=None, seed=1234, pin=False):
+    """Synthetic 3-frame triplets of the named HxW: U[0,1) images, KITTI-normalised K, pinv(K)."""
+    import numpy as np
+    B, H, W = opt.batch_size, opt.height, opt.width
+    g = torch.Generator().manual_seed(seed)
+    inputs = {}
+    for f in (-1, 0, 1):
+        inputs[("color", f, 0)] = torch.rand(B, 3, H, W, generator=g)
+        inputs[("color_aug", f, 0)] = torch.rand(B, 3, H, W, generator=g)
+    K = np.array([[0.58 * W, 0, 0.5 * W, 0], [0, 1.92 * H, 0.5 * H, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float32)
+    inv_K = np.linalg.pinv(K)
+    inputs[("K", 0)] = torch.from_numpy(np.repeat(K[None], B, 0).copy())
+    inputs[("inv_K", 0)] = torch.from_numpy(np.repeat(inv_K[None], B, 0).astype(np.float32).copy())
+    if pin:
+        inputs = {k: v.pin_memory() for k, v in inputs.items()}
+    if device is not None:
+        inputs = {k: v.to(device) for k, v in inputs.items()}
+    return inputs
