@@ -120,6 +120,10 @@ int mvf_si_log_fwd(const float* pred, const float* target, const float* mask, fl
 int mvf_si_log_bwd(const float* pred, const float* target, const float* mask, const float* stats, const float* gout,
                    float* g_pred, float* g_target, int B, size_t HW, float beta, void* stream);
 
+/* device self-test: q_sequence[i] = the kernels' shared-reciprocal division of a[i] by b[i], q_ieee[i] = the
+ * IEEE quotient (div.rn.f32); the two must be bit-identical for operands in the normal range. */
+int mvf_selftest_division(const float* a, const float* b, float* q_sequence, float* q_ieee, size_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,7 @@ SIGNATURES = {
     "mvf_smooth_loss_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mvf_si_log_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _sz, _f, _vp]),
     "mvf_si_log_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _sz, _f, _vp]),
+    "mvf_selftest_division": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -138,45 +138,70 @@ __global__ void __maxnreg__(112) f1_fwd_kernel(const F1Args a) {
         const float* __restrict__ tgtb = a.tgt + (size_t)b * 3 * HW;
         const float* __restrict__ s0b = a.src0 + (size_t)b * 3 * HW;
         const float* __restrict__ s1b = a.src1 + (size_t)b * 3 * HW;
-        for (int p = tid; p < HHT * HWD; p += NT) {
+        // Three passes over this thread's (up to NPOS) halo positions so that independent global loads are issued
+        // back to back: (a) disparity, (b) geometry -> corner blocks, (c) gathers + direct loads -> shared memory.
+        constexpr int NPOS = (HHT * HWD + NT - 1) / NT;
+        int pi[NPOS];      // pixel offset of the (reflected) position inside the image
+        float dv[NPOS];
+        Corner c0[NPOS], c1[NPOS];
+#pragma unroll
+        for (int j = 0; j < NPOS; ++j) {
+            const int p = min(tid + j * NT, HHT * HWD - 1);
+            const int hy = p / HWD, hx = p - hy * HWD;
+            const int y = clampi(reflect1(ty0 - 1 + hy, H), 0, H - 1), x = clampi(reflect1(tx0 - 1 + hx, W), 0, W - 1);
+            pi[j] = y * W + x;
+            dv[j] = __ldg(dispb + pi[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < NPOS; ++j) {
+            const int p = min(tid + j * NT, HHT * HWD - 1);
             const int hy = p / HWD, hx = p - hy * HWD;
             const int ry = ty0 - 1 + hy, rx = tx0 - 1 + hx;    // raw (possibly padded / out-of-image) coords
-            const int y = clampi(reflect1(ry, H), 0, H - 1), x = clampi(reflect1(rx, W), 0, W - 1);
-            const int i = y * W + x;
-            const float d = __ldg(dispb + i);
-            float tv[3], sv0[3], sv1[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                tv[c] = __ldg(tgtb + (i + c * HWi));
-                sv0[c] = __ldg(s0b + (i + c * HWi));
-                sv1[c] = __ldg(s1b + (i + c * HWi));
-            }
-            const float depth = disp_to_depth(d, a.min_disp, a.disp_range);
+            const int y = pi[j] / W, x = pi[j] - y * W;
+            const float depth = disp_to_depth(dv[j], a.min_disp, a.disp_range);
             float cr[3], X[3], pr[3];
             cam_ray(sm.cst, (float)x, (float)y, cr);
             Tap t0, t1;
             project_tap(depth, cr, sm.cst + 12, g, t0, X, pr);
             project_tap(depth, cr, sm.cst + 24, g, t1, X, pr);
-            float w0[3], w1[3];
-            gather3(s0b, HWi, W, corner_of(t0, H, W), w0);
-            gather3(s1b, HWi, W, corner_of(t1, H, W), w1);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                sm.T2[c][hy][hx] = make_float2(tv[c], tv[c]);
-                sm.S[c][hy][hx] = make_float2(sv0[c], sv1[c]);
-                sm.Wp[c][hy][hx] = make_float2(w0[c], w1[c]);
-            }
-            if (hy >= 1 && hx >= 1) sm.D[hy - 1][hx - 1] = d;
+            c0[j] = corner_of(t0, H, W);
+            c1[j] = corner_of(t1, H, W);
             if (a.x0y0 != nullptr && ry == y && rx == x && hy >= 1 && hy <= TH && hx >= 1 && hx <= TW) {
-                size_t n = (size_t)a.B * HW, o = (size_t)b * HW + i;
+                size_t n = (size_t)a.B * HW, o = (size_t)b * HW + pi[j];
                 a.x0y0[o] = t0.x0;
                 a.x0y0[n + o] = t0.y0;
                 a.x0y0[2 * n + o] = t1.x0;
                 a.x0y0[3 * n + o] = t1.y0;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NPOS; ++j) {
+            const int p = tid + j * NT;
+            if (p < HHT * HWD) {
+                const int hy = p / HWD, hx = p - hy * HWD;
+                const int i = pi[j];
+                float tv[3], sv0[3], sv1[3], w0[3], w1[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    a.warp0[((size_t)b * 3 + c) * HW + i] = w0[c];
-                    a.warp1[((size_t)b * 3 + c) * HW + i] = w1[c];
+                    tv[c] = __ldg(tgtb + (i + c * HWi));
+                    sv0[c] = __ldg(s0b + (i + c * HWi));
+                    sv1[c] = __ldg(s1b + (i + c * HWi));
+                }
+                gather3(s0b, HWi, W, c0[j], w0);
+                gather3(s1b, HWi, W, c1[j], w1);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    sm.T2[c][hy][hx] = make_float2(tv[c], tv[c]);
+                    sm.S[c][hy][hx] = make_float2(sv0[c], sv1[c]);
+                    sm.Wp[c][hy][hx] = make_float2(w0[c], w1[c]);
+                }
+                if (hy >= 1 && hx >= 1) sm.D[hy - 1][hx - 1] = dv[j];
+                if (a.warp0 != nullptr && hy >= 1 && hy <= TH && hx >= 1 && hx <= TW && ty0 - 1 + hy < H && tx0 - 1 + hx < W) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        a.warp0[((size_t)b * 3 + c) * HW + i] = w0[c];
+                        a.warp1[((size_t)b * 3 + c) * HW + i] = w1[c];
+                    }
                 }
             }
         }
