@@ -43,7 +43,8 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % s)
     # cudart (and, for the conv kernels' tensor maps, the driver API) are linked dynamically
-    subprocess.check_call([NVCC, "-shared", "-o", SO] + objs + ["-lcudart", "-lcuda"])
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + objs +
+                          ["-lcudart", "-lcuda"])
     return SO
 
 
