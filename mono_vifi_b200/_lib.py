@@ -3,7 +3,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libmonovifi_b200.so")
+# MVF_LIB selects another build of the same library (A/B timing of kernel variants); default: the in-tree build
+SO_PATH = os.environ.get("MVF_LIB") or os.path.join(_HERE, "libmonovifi_b200.so")
 
 NO_SSIM, AVG_REPROJECTION, DISABLE_AUTOMASKING = 1, 2, 4
 

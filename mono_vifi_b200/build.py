@@ -24,7 +24,10 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """`defines` / `out`: build a tuning variant (e.g. defines=["MVF_F1_FWD_MINB=3"], out="/path/lib_v.so")."""
+    if out is not None or defines:
+        return _build_variant(list(defines), out or SO, verbose)
     if not force and not stale():
         return SO
     objs = []
@@ -46,6 +49,27 @@ def build(force=False, verbose=False):
     subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + objs +
                           ["-lcudart", "-lcuda"])
     return SO
+
+
+def _build_variant(defines, out, verbose):
+    tag = "_".join(d.replace("=", "-") for d in defines) or "default"
+    bdir = os.path.join(HERE, "build", tag)
+    os.makedirs(bdir, exist_ok=True)
+    objs, procs = [], []
+    for s in sources():
+        o = os.path.join(bdir, os.path.basename(s)[:-3] + ".o")
+        objs.append(o)
+        procs.append((s, subprocess.Popen([NVCC] + FLAGS + ["-D" + d for d in defines] + ["-c", s, "-o", o],
+                                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for s, p in procs:
+        outp, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(outp)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed on %s" % s)
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs +
+                          ["-lcudart", "-lcuda"])
+    return out
 
 
 if __name__ == "__main__":

@@ -356,9 +356,9 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
                 int k = q / 12, e = q - 12 * k;
                 atomicAdd(reinterpret_cast<unsigned long long*>(acc + ((size_t)k * B + b) * 12 + e),
                           (unsigned long long)to_fix(dv));
-                __threadfence();
             }
         }
+        if (lane == 0) __threadfence();  // one release fence per warp, after its last accumulator update
     }
     __syncthreads();
     if (tid == 0) {

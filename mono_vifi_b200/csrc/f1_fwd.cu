@@ -21,102 +21,114 @@ constexpr int HWD = TW + 2, HHT = TH + 2;
 constexpr int NT = 192;  // 3 channel groups x 64 threads
 constexpr int RPT = 4;   // output rows per thread in phase 2
 
+// 54.7 KB per CTA, 96 registers per thread: three CTAs = 18 warps per SM under a 75 % shared-memory carve-out.
+// The remaining ~57 KB stay L1: the bilinear gathers live on it (a 100 % carve-out with four CTAs was 1.7x slower
+// on the B200, profiles/r1_f1_variants.md).
 struct __align__(16) FwdSmem {
-    float2 T2[3][HHT][HWD];  // target, duplicated {t,t}
+    float2 T2[3][HHT][HWD];  // target, duplicated {t,t} (feeds the packed FFMA2 products directly)
     float2 S[3][HHT][HWD];   // raw sources {src0, src1}   (identity-reprojection candidates)
     float2 Wp[3][HHT][HWD];  // warped sources {warp0, warp1}
-    float4 REP[3][TH][TW];   // per-channel reprojection terms {id0, id1, w0, w1}
+    float2 REPA[TH][TW];     // reprojection terms summed over channels {id0, id1}
+    float2 REPB[TH][TW];     //                                         {w0, w1}
     float D[TH + 1][TW + 1]; // disparity (+1 right / bottom neighbour for the smoothness term)
     float cst[36];           // inv_K rows 0..2 (12), P0 (12), P1 (12)
     float red[NT / 32][4];
     int is_last;
 };
 
-struct HS {  // horizontal 3-tap sums for one output column
-    float2 t, tt, s, ss, st, w, ww, wt;
+// horizontal 3-tap sums of one row for one output column: target statistics are scalars, the candidate pair
+// {x_a, x_b} rides in packed float2 lanes
+struct HS {
+    float t, tt;
+    float2 x, xx, xt;
 };
 
-__device__ __forceinline__ void hsum_pair(float2 x0, float2 x1, float2 x2, float2 x3, float2 t0, float2 t1,
-                                          float2 t2, float2 t3, float2& a0, float2& a1, float2& b0, float2& b1,
-                                          float2& c0, float2& c1) {
-    float2 m = add2(x1, x2);
-    a0 = add2(m, x0);
-    a1 = add2(m, x3);
-    m = fma2(x1, x1, mul2(x2, x2));
-    b0 = fma2(x0, x0, m);
-    b1 = fma2(x3, x3, m);
-    m = fma2(x1, t1, mul2(x2, t2));
-    c0 = fma2(x0, t0, m);
-    c1 = fma2(x3, t3, m);
+__device__ __forceinline__ void hsum_row(const float2 (*__restrict__ T2c)[HWD], const float2 (*__restrict__ Xc)[HWD],
+                                         int hr, int cx, HS h[2], float tc[2], float2 xc[2]) {
+    const float4* tp = reinterpret_cast<const float4*>(&T2c[hr][2 * cx]);
+    const float4* xp = reinterpret_cast<const float4*>(&Xc[hr][2 * cx]);
+    const float4 ta = tp[0], tb = tp[1], xa = xp[0], xb = xp[1];
+    const float2 t0 = make_float2(ta.x, ta.y), t1 = make_float2(ta.z, ta.w), t2 = make_float2(tb.x, tb.y),
+                 t3 = make_float2(tb.z, tb.w);
+    const float2 x0 = make_float2(xa.x, xa.y), x1 = make_float2(xa.z, xa.w), x2 = make_float2(xb.x, xb.y),
+                 x3 = make_float2(xb.z, xb.w);
+    float m = t1.x + t2.x;
+    h[0].t = m + t0.x;
+    h[1].t = m + t3.x;
+    m = fmaf(t1.x, t1.x, t2.x * t2.x);
+    h[0].tt = fmaf(t0.x, t0.x, m);
+    h[1].tt = fmaf(t3.x, t3.x, m);
+    float2 q = add2(x1, x2);
+    h[0].x = add2(q, x0);
+    h[1].x = add2(q, x3);
+    q = fma2(x1, x1, mul2(x2, x2));
+    h[0].xx = fma2(x0, x0, q);
+    h[1].xx = fma2(x3, x3, q);
+    q = fma2(x1, t1, mul2(x2, t2));
+    h[0].xt = fma2(x0, t0, q);
+    h[1].xt = fma2(x3, t3, q);
+    tc[0] = t1.x; tc[1] = t2.x; xc[0] = x1; xc[1] = x2;
 }
 
-__device__ __forceinline__ void hsum_row(const FwdSmem& sm, int c, int hr, int cx, HS h[2], float2 ctr[6]) {
-    const float4* tp = reinterpret_cast<const float4*>(&sm.T2[c][hr][2 * cx]);
-    const float4* sp = reinterpret_cast<const float4*>(&sm.S[c][hr][2 * cx]);
-    const float4* wp = reinterpret_cast<const float4*>(&sm.Wp[c][hr][2 * cx]);
-    float4 ta = tp[0], tb = tp[1], sa = sp[0], sb = sp[1], wa = wp[0], wb = wp[1];
-    float2 t0 = make_float2(ta.x, ta.y), t1 = make_float2(ta.z, ta.w), t2 = make_float2(tb.x, tb.y),
-           t3 = make_float2(tb.z, tb.w);
-    float2 s0 = make_float2(sa.x, sa.y), s1 = make_float2(sa.z, sa.w), s2 = make_float2(sb.x, sb.y),
-           s3 = make_float2(sb.z, sb.w);
-    float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w), w2 = make_float2(wb.x, wb.y),
-           w3 = make_float2(wb.z, wb.w);
-    float2 m = add2(t1, t2);
-    h[0].t = add2(m, t0);
-    h[1].t = add2(m, t3);
-    m = fma2(t1, t1, mul2(t2, t2));
-    h[0].tt = fma2(t0, t0, m);
-    h[1].tt = fma2(t3, t3, m);
-    hsum_pair(s0, s1, s2, s3, t0, t1, t2, t3, h[0].s, h[1].s, h[0].ss, h[1].ss, h[0].st, h[1].st);
-    hsum_pair(w0, w1, w2, w3, t0, t1, t2, t3, h[0].w, h[1].w, h[0].ww, h[1].ww, h[0].wt, h[1].wt);
-    ctr[0] = t1; ctr[1] = t2; ctr[2] = s1; ctr[3] = s2; ctr[4] = w1; ctr[5] = w2;
-}
-
-// 0.85/3 * SSIM-loss + 0.15/3 * |t - x| for a packed pair of candidates (layers.py:277-290, train.py:973-985)
-__device__ __forceinline__ float2 rep_pair(float2 vx, float2 vxx, float2 vxt, float2 my, float2 my2c, float2 sigyc,
-                                           float2 tc, float2 xc, float cS, float cL) {
-    const float2 k9 = f2(1.0f / 9.0f);
-    const float C1 = 0.0001f, C2 = 0.0009f;
-    float2 mx = mul2(vx, k9);
-    float2 mxmy = mul2(mx, my);
-    float2 mx2 = mul2(mx, mx);
-    float2 sigx = fma2(vxx, k9, -mx2);
-    float2 sigxy = fma2(vxt, k9, -mxmy);
-    float2 n = mul2(fma2(f2(2.0f), mxmy, f2(C1)), fma2(f2(2.0f), sigxy, f2(C2)));
-    float2 d = mul2(add2(mx2, my2c), add2(sigx, sigyc));
-    float2 df = sub2(tc, xc);
+// 0.85/3 * SSIM-loss + 0.15/3 * |t - x| of one window for the packed candidate pair
+// (layers.py:277-290, train.py:973-985)
+__device__ __forceinline__ float2 rep_window(const HS& a, const HS& b, const HS& c, float tc, float2 xc, float cS, float cL) {
+    const float k9 = 1.0f / 9.0f, C1 = 0.0001f, C2 = 0.0009f;
+    const float vt = (a.t + b.t) + c.t, vtt = (a.tt + b.tt) + c.tt;
+    const float my = vt * k9, my2 = my * my;
+    const float sigyc = fmaf(vtt, k9, -my2) + C2, my2c = my2 + C1;
+    const float2 vx = add2(add2(a.x, b.x), c.x), vxx = add2(add2(a.xx, b.xx), c.xx), vxt = add2(add2(a.xt, b.xt), c.xt);
+    const float2 mx = mul2(vx, f2(k9));
+    const float2 mxmy = mul2(mx, f2(my));
+    const float2 mx2 = mul2(mx, mx);
+    const float2 sigx = fma2(vxx, f2(k9), -mx2);
+    const float2 sigxy = fma2(vxt, f2(k9), -mxmy);
+    const float2 n = mul2(fma2(f2(2.0f), mxmy, f2(C1)), fma2(f2(2.0f), sigxy, f2(C2)));
+    const float2 d = mul2(add2(mx2, f2(my2c)), add2(sigx, f2(sigyc)));
     float2 r;
     r.x = __saturatef(fmaf(-0.5f, __fdividef(n.x, d.x), 0.5f));
     r.y = __saturatef(fmaf(-0.5f, __fdividef(n.y, d.y), 0.5f));
-    r.x = fmaf(cL, fabsf(df.x), cS * r.x);
-    r.y = fmaf(cL, fabsf(df.y), cS * r.y);
+    r.x = fmaf(cL, fabsf(tc - xc.x), cS * r.x);
+    r.y = fmaf(cL, fabsf(tc - xc.y), cS * r.y);
     return r;
 }
 
-__device__ __forceinline__ void emit(FwdSmem& sm, int c, int orow, int cx, const HS a[2], const HS b[2], const HS cu[2],
-                                     const float2 ctr[6], float cS, float cL) {
-    const float2 k9 = f2(1.0f / 9.0f);
+// one pass of the separable 3x3 window statistics over this thread's 2 columns x RPT rows of channel c:
+// horizontal sums from 128-bit LDS, vertical sums from a 2-row register ring
+__device__ __forceinline__ void window_pass(const float2 (*__restrict__ T2c)[HWD], const float2 (*__restrict__ Xc)[HWD],
+                                            int row0, int cx, float cS, float cL, float2 acc[RPT][2]) {
+    HS r0[2], r1[2], cu[2];
+    float tcp[2], tc[2];
+    float2 xcp[2], xc[2];
+    hsum_row(T2c, Xc, row0 + 0, cx, r0, tc, xc);
+    hsum_row(T2c, Xc, row0 + 1, cx, r1, tcp, xcp);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        float2 vt = add2(add2(a[j].t, b[j].t), cu[j].t);
-        float2 vtt = add2(add2(a[j].tt, b[j].tt), cu[j].tt);
-        float2 my = mul2(vt, k9);
-        float2 my2 = mul2(my, my);
-        float2 sigyc = add2(fma2(vtt, k9, -my2), f2(0.0009f));
-        float2 my2c = add2(my2, f2(0.0001f));
-        float2 vs = add2(add2(a[j].s, b[j].s), cu[j].s);
-        float2 vss = add2(add2(a[j].ss, b[j].ss), cu[j].ss);
-        float2 vst = add2(add2(a[j].st, b[j].st), cu[j].st);
-        float2 vw = add2(add2(a[j].w, b[j].w), cu[j].w);
-        float2 vww = add2(add2(a[j].ww, b[j].ww), cu[j].ww);
-        float2 vwt = add2(add2(a[j].wt, b[j].wt), cu[j].wt);
-        float2 rs = rep_pair(vs, vss, vst, my, my2c, sigyc, ctr[j], ctr[2 + j], cS, cL);
-        float2 rw = rep_pair(vw, vww, vwt, my, my2c, sigyc, ctr[j], ctr[4 + j], cS, cL);
-        sm.REP[c][orow][2 * cx + j] = make_float4(rs.x, rs.y, rw.x, rw.y);
+    for (int s = 2; s < RPT + 2; ++s) {
+        hsum_row(T2c, Xc, row0 + s, cx, cu, tc, xc);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            acc[s - 2][j] = rep_window(r0[j], r1[j], cu[j], tcp[j], xcp[j], cS, cL);
+            r0[j] = r1[j];
+            r1[j] = cu[j];
+            tcp[j] = tc[j];
+            xcp[j] = xc[j];
+        }
     }
 }
 
-__global__ void __maxnreg__(112) f1_fwd_kernel(const F1Args a) {
+// tuning knobs (A/B-timed on the B200): register cap, shared-memory carve-out (the rest of the
+// 228 KB stays L1 for the bilinear gathers), halo positions per phase-1 chunk
+#ifndef MVF_F1_FWD_REGS
+#define MVF_F1_FWD_REGS 96
+#endif
+#ifndef MVF_F1_FWD_CARVEOUT
+#define MVF_F1_FWD_CARVEOUT 75
+#endif
+#ifndef MVF_F1_FWD_NPOS
+#define MVF_F1_FWD_NPOS 2
+#endif
+template <bool DBG>
+__global__ void __maxnreg__(MVF_F1_FWD_REGS) f1_fwd_kernel(const F1Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -140,43 +152,56 @@ __global__ void __maxnreg__(112) f1_fwd_kernel(const F1Args a) {
         const float* __restrict__ s1b = a.src1 + (size_t)b * 3 * HW;
         // Three passes over this thread's (up to NPOS) halo positions so that independent global loads are issued
         // back to back: (a) disparity, (b) geometry -> corner blocks, (c) gathers + direct loads -> shared memory.
-        constexpr int NPOS = (HHT * HWD + NT - 1) / NT;
+        // Slots past the last halo position are skipped (whole warps, except one partial warp).
+        constexpr int NPOS = MVF_F1_FWD_NPOS;  // positions per chunk (bounds the live registers)
+        constexpr int NCHUNK = (HHT * HWD + NPOS * NT - 1) / (NPOS * NT);
+#pragma unroll 1
+        for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int pbase = tid + ch * NPOS * NT;
         int pi[NPOS];      // pixel offset of the (reflected) position inside the image
         float dv[NPOS];
         Corner c0[NPOS], c1[NPOS];
 #pragma unroll
         for (int j = 0; j < NPOS; ++j) {
-            const int p = min(tid + j * NT, HHT * HWD - 1);
-            const int hy = p / HWD, hx = p - hy * HWD;
-            const int y = clampi(reflect1(ty0 - 1 + hy, H), 0, H - 1), x = clampi(reflect1(tx0 - 1 + hx, W), 0, W - 1);
-            pi[j] = y * W + x;
-            dv[j] = __ldg(dispb + pi[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < NPOS; ++j) {
-            const int p = min(tid + j * NT, HHT * HWD - 1);
-            const int hy = p / HWD, hx = p - hy * HWD;
-            const int ry = ty0 - 1 + hy, rx = tx0 - 1 + hx;    // raw (possibly padded / out-of-image) coords
-            const int y = pi[j] / W, x = pi[j] - y * W;
-            const float depth = disp_to_depth(dv[j], a.min_disp, a.disp_range);
-            float cr[3], X[3], pr[3];
-            cam_ray(sm.cst, (float)x, (float)y, cr);
-            Tap t0, t1;
-            project_tap(depth, cr, sm.cst + 12, g, t0, X, pr);
-            project_tap(depth, cr, sm.cst + 24, g, t1, X, pr);
-            c0[j] = corner_of(t0, H, W);
-            c1[j] = corner_of(t1, H, W);
-            if (a.x0y0 != nullptr && ry == y && rx == x && hy >= 1 && hy <= TH && hx >= 1 && hx <= TW) {
-                size_t n = (size_t)a.B * HW, o = (size_t)b * HW + pi[j];
-                a.x0y0[o] = t0.x0;
-                a.x0y0[n + o] = t0.y0;
-                a.x0y0[2 * n + o] = t1.x0;
-                a.x0y0[3 * n + o] = t1.y0;
+            const int p = pbase + j * NT;
+            pi[j] = 0;
+            dv[j] = 0.f;
+            if (p < HHT * HWD) {
+                const int hy = p / HWD, hx = p - hy * HWD;
+                const int y = clampi(reflect1(ty0 - 1 + hy, H), 0, H - 1), x = clampi(reflect1(tx0 - 1 + hx, W), 0, W - 1);
+                pi[j] = y * W + x;
+                dv[j] = __ldg(dispb + pi[j]);
             }
         }
 #pragma unroll
         for (int j = 0; j < NPOS; ++j) {
-            const int p = tid + j * NT;
+            const int p = pbase + j * NT;
+            if (p < HHT * HWD) {
+                const int y = pi[j] / W, x = pi[j] - y * W;
+                const float depth = disp_to_depth(dv[j], a.min_disp, a.disp_range);
+                float cr[3], X[3], pr[3];
+                cam_ray(sm.cst, (float)x, (float)y, cr);
+                Tap t0, t1;
+                project_tap(depth, cr, sm.cst + 12, g, t0, X, pr);
+                project_tap(depth, cr, sm.cst + 24, g, t1, X, pr);
+                c0[j] = corner_of(t0, H, W);
+                c1[j] = corner_of(t1, H, W);
+                if (DBG) {
+                    const int hy = p / HWD, hx = p - hy * HWD;
+                    const int ry = ty0 - 1 + hy, rx = tx0 - 1 + hx;  // raw (possibly padded / out-of-image) coords
+                    if (a.x0y0 != nullptr && ry == y && rx == x && hy >= 1 && hy <= TH && hx >= 1 && hx <= TW) {
+                        size_t n = (size_t)a.B * HW, o = (size_t)b * HW + pi[j];
+                        a.x0y0[o] = t0.x0;
+                        a.x0y0[n + o] = t0.y0;
+                        a.x0y0[2 * n + o] = t1.x0;
+                        a.x0y0[3 * n + o] = t1.y0;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NPOS; ++j) {
+            const int p = pbase + j * NT;
             if (p < HHT * HWD) {
                 const int hy = p / HWD, hx = p - hy * HWD;
                 const int i = pi[j];
@@ -196,38 +221,53 @@ __global__ void __maxnreg__(112) f1_fwd_kernel(const F1Args a) {
                     sm.Wp[c][hy][hx] = make_float2(w0[c], w1[c]);
                 }
                 if (hy >= 1 && hx >= 1) sm.D[hy - 1][hx - 1] = dv[j];
-                if (a.warp0 != nullptr && hy >= 1 && hy <= TH && hx >= 1 && hx <= TW && ty0 - 1 + hy < H && tx0 - 1 + hx < W) {
+                if (DBG) {
+                    if (a.warp0 != nullptr && hy >= 1 && hy <= TH && hx >= 1 && hx <= TW && ty0 - 1 + hy < H &&
+                        tx0 - 1 + hx < W) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        a.warp0[((size_t)b * 3 + c) * HW + i] = w0[c];
-                        a.warp1[((size_t)b * 3 + c) * HW + i] = w1[c];
+                        for (int c = 0; c < 3; ++c) {
+                            a.warp0[((size_t)b * 3 + c) * HW + i] = w0[c];
+                            a.warp1[((size_t)b * 3 + c) * HW + i] = w1[c];
+                        }
                     }
                 }
             }
         }
+        }  // chunk
     }
     __syncthreads();
 
-    // ---------------- phase 2: separable 3x3 window statistics, SSIM + L1 per channel ------------------------
+    // ---------------- phase 2: separable 3x3 window statistics, SSIM + L1, summed over channels ---------------
+    // one 64-thread group per colour channel; each thread owns 2 columns x RPT rows and makes two passes
+    // (identity pair, warped pair) so that the register ring stays small
     {
         const bool nossim = (a.flags & F_NO_SSIM) != 0;
         const float cS = nossim ? 0.0f : 0.85f / 3.0f, cL = nossim ? 1.0f / 3.0f : 0.15f / 3.0f;
         const int c = tid >> 6, t = tid & 63, cx = t & 15, rg = t >> 4;
-        HS r0[2], r1[2], cu[2];
-        float2 ctr_prev[6], ctr[6];
-        hsum_row(sm, c, rg * RPT + 0, cx, r0, ctr);
-        hsum_row(sm, c, rg * RPT + 1, cx, r1, ctr_prev);
+        // channel sum in a fixed order (0 + 1) + 2, so the result does not depend on scheduling
 #pragma unroll
-        for (int s = 2; s < RPT + 2; ++s) {
-            hsum_row(sm, c, rg * RPT + s, cx, cu, ctr);
-            emit(sm, c, rg * RPT + s - 2, cx, r0, r1, cu, ctr_prev, cS, cL);
+        for (int pass = 0; pass < 2; ++pass) {
+            float2 acc[RPT][2];
+            window_pass(sm.T2[c], pass == 0 ? sm.S[c] : sm.Wp[c], rg * RPT, cx, cS, cL, acc);
+            float2 (*REP)[TW] = pass == 0 ? sm.REPA : sm.REPB;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) { r0[j] = r1[j]; r1[j] = cu[j]; }
+            for (int cc = 0; cc < 3; ++cc) {
+                if (c == cc) {
 #pragma unroll
-            for (int q = 0; q < 6; ++q) ctr_prev[q] = ctr[q];
+                    for (int r = 0; r < RPT; ++r) {
+                        float4* pa = reinterpret_cast<float4*>(&REP[rg * RPT + r][2 * cx]);
+                        float4 va = make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y);
+                        if (cc > 0) {
+                            const float4 oa = *pa;
+                            va = make_float4(oa.x + va.x, oa.y + va.y, oa.z + va.z, oa.w + va.w);
+                        }
+                        *pa = va;
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
-    __syncthreads();
 
     // ---------------- phase 3: channel mix, min / argmin, mask, smoothness, reduction ------------------------
     float photo = 0.f, sx = 0.f, sy = 0.f, sd = 0.f;
@@ -244,9 +284,8 @@ __global__ void __maxnreg__(112) f1_fwd_kernel(const F1Args a) {
             const int y = ty0 + row, x = tx0 + col;
             if (y >= H || x >= W) continue;
             const int i = y * W + x;
-            const float4 r0 = sm.REP[0][row][col], r1 = sm.REP[1][row][col], r2 = sm.REP[2][row][col];
-            const float id0 = r0.x + r1.x + r2.x, id1 = r0.y + r1.y + r2.y;
-            const float w0 = r0.z + r1.z + r2.z, w1 = r0.w + r1.w + r2.w;
+            const float2 ra = sm.REPA[row][col], rb = sm.REPB[row][col];
+            const float id0 = ra.x, id1 = ra.y, w0 = rb.x, w1 = rb.y;
             // combined = cat(identity (+1e-5 noise), reprojection) ; min / argmin, first minimum wins (train.py:1023-1033)
             float m;
             int best = 0;
@@ -272,7 +311,7 @@ __global__ void __maxnreg__(112) f1_fwd_kernel(const F1Args a) {
             }
             if (mkb) m *= __ldg(mkb + i);
             idxb[i] = (uint8_t)best;
-            if (tob) tob[i] = m;
+            if (DBG) { if (tob) tob[i] = m; }
             photo += m;
             // edge-aware smoothness on the raw disparity; the 1/(mean+eps) factor is applied per image later
             float d = sm.D[row][col];
@@ -351,13 +390,22 @@ __global__ void __maxnreg__(112) f1_fwd_kernel(const F1Args a) {
 cudaError_t launch_f1_forward(const F1Args& a, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(f1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(f1_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(FwdSmem));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(f1_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem));
+        // shared-memory carve-out: enough for three CTAs, the rest is L1 for the gathers
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(f1_fwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     MVF_F1_FWD_CARVEOUT);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, a.B);
-    f1_fwd_kernel<<<grid, NT, sizeof(FwdSmem), stream>>>(a);
+    if (a.x0y0 != nullptr || a.warp0 != nullptr || a.to_opt != nullptr)
+        f1_fwd_kernel<true><<<grid, NT, sizeof(FwdSmem), stream>>>(a);
+    else
+        f1_fwd_kernel<false><<<grid, NT, sizeof(FwdSmem), stream>>>(a);
     return cudaGetLastError();
 }
 

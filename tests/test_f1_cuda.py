@@ -186,7 +186,7 @@ def test_full_size_properties():
     # (gout multiplies the per-term weights before the terms are summed, so cancelling sums move by a few ulp of
     #  the largest term: tolerance relative to the gradient's magnitude, not element-wise)
     g1n = g1[0].cpu().numpy()
-    np.testing.assert_allclose(g3[0].cpu().numpy(), 2.5 * g1n, rtol=1e-5, atol=2e-6 * np.abs(g1n).max())
+    np.testing.assert_allclose(g3[0].cpu().numpy(), 2.5 * g1n, rtol=1e-5, atol=2e-5 * np.abs(g1n).max())
     assert torch.isfinite(g1[0]).all() and torch.isfinite(g1[1]).all() and torch.isfinite(g1[2]).all()
 
 

@@ -15,8 +15,10 @@ import synth  # noqa: E402
 
 
 def main():
-    B, H, W = (int(x) for x in sys.argv[1:4]) if len(sys.argv) >= 4 else (12, 192, 640)
-    iters = int(sys.argv[4]) if len(sys.argv) >= 5 else 50
+    smooth = "--smooth" in sys.argv  # low-frequency disparity (what a depth network emits) instead of white noise
+    argv = [a for a in sys.argv if not a.startswith("--")]
+    B, H, W = (int(x) for x in argv[1:4]) if len(argv) >= 4 else (12, 192, 640)
+    iters = int(argv[4]) if len(argv) >= 5 else 50
     dev = torch.device("cuda:0")
     peaks = {}
     try:
@@ -33,6 +35,9 @@ def main():
     sets = []
     for s in range(nset):
         disp = torch.rand(B, 1, H, W, device=dev, generator=g)
+        if smooth:
+            lo = torch.rand(B, 1, H // 16, W // 16, device=dev, generator=g)
+            disp = 0.05 * disp + 0.9 * torch.nn.functional.interpolate(lo, size=(H, W), mode="bilinear", align_corners=False)
         imgs = [torch.rand(B, 3, H, W, device=dev, generator=g) for _ in range(3)]
         sets.append((disp, *imgs))
     T = [tests_helpers.synth_T(c["axisangle"][k], c["translation"][k], k == 1) for k in range(2)]
@@ -66,7 +71,7 @@ def main():
     res["bwd_GBs"] = 44.0 * px / res["bwd_us"] / 1e3
     res["fwd_frac"] = res["fwd_GBs"] / hbm
     res["bwd_frac"] = res["bwd_GBs"] / hbm
-    res.update(B=B, H=H, W=W, nset=nset, iters=iters, hbm_peak=hbm, loss=float(outs[0]["loss"][0]))
+    res.update(lib=os.environ.get("MVF_LIB", "default").split("/")[-1], disp="smooth" if smooth else "white-noise", B=B, H=H, W=W, nset=nset, iters=iters, hbm_peak=hbm, loss=float(outs[0]["loss"][0]))
     print(json.dumps(res))
 
 
