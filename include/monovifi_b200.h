@@ -120,9 +120,40 @@ int mvf_si_log_fwd(const float* pred, const float* target, const float* mask, fl
 int mvf_si_log_bwd(const float* pred, const float* target, const float* mask, const float* stats, const float* gout,
                    float* g_pred, float* g_target, int B, size_t HW, float beta, void* stream);
 
+/* ---- tensor-core convolutions (tcgen05 / TMEM / TMA implicit GEMM, TF32 inputs, fp32 accumulate) ----------------
+ * Replace the cuDNN calls behind nn.Conv2d in the reference's networks (layers.py:131,146 Conv3x3 / Conv1x1;
+ * networks/monodepth2.py:16-96, networks/posenet.py:10-137 via torchvision ResNet) on CHANNELS-LAST fp32 tensors
+ * (NCHW-shaped torch tensors in torch.channels_last memory format: element (b,c,y,x) at b*sB + y*sH + x*sW + c).
+ * The filter bank is re-packed once per weight update with mvf_conv2d_pack_filters (dgrad = 0: forward;
+ * dgrad = 1: the flipped / transposed bank, with which mvf_conv2d_forward on grad_out and pad' = k-1-pad computes
+ * the input gradient of a stride-1 convolution).  Strides are in elements; the channel stride is 1.
+ * Constraints (mvf_conv2d_supported): stride 1 or 2, Cin % 4 == 0, strides % 4 == 0, pointers 16-byte aligned. */
+typedef struct {
+    int B, Cin, H, W;               /* input  [B,Cin,H,W]  */
+    int Cout, KH, KW, pad, stride;  /* output [B,Cout,(H+2pad-KH)/stride+1,(W+2pad-KW)/stride+1] */
+    long long x_stride[3];          /* batch, row (y), column (x) */
+    long long y_stride[3];
+} mvf_conv2d_desc;
+#define MVF_ACT_NONE 0
+#define MVF_ACT_RELU 1
+#define MVF_ACT_ELU 2
+size_t mvf_conv2d_packed_filter_floats(int N, int K, int KH, int KW);
+int mvf_conv2d_pack_filters(const float* w /*[Cout,Cin,KH,KW]*/, float* packed, int Cout, int Cin, int KH, int KW,
+                            int dgrad, void* stream);
+int mvf_conv2d_supported(const mvf_conv2d_desc* d); /* 1 / 0 (reason in mvf_last_error) */
+int mvf_conv2d_forward(const mvf_conv2d_desc* d, const float* x, const float* w_packed, const float* bias /*or NULL*/,
+                       float* y, int act, void* stream);
+
 /* device self-test: q_sequence[i] = the kernels' shared-reciprocal division of a[i] by b[i], q_ieee[i] = the
  * IEEE quotient (div.rn.f32); the two must be bit-identical for operands in the normal range. */
 int mvf_selftest_division(const float* a, const float* b, float* q_sequence, float* q_ieee, size_t n, void* stream);
+
+/* device self-test of the tcgen05 plumbing: D[128,N] = A . B^T on one CTA (TF32 in, fp32 out).  A is [128][K]
+ * (a_mn_major = 0) or [K][128] (a_mn_major = 1, the layout NCHW activations have); B is [N][K].
+ * K % 32 == 0, N % 16 == 0, 16 <= N <= 256. */
+int mvf_selftest_umma(const float* A, const float* B, float* D, int N, int K, int a_mn_major, void* stream);
+/* development aid: when non-NULL, CTA (0,0) of mvf_conv2d_forward dumps its pipeline stage 0 there */
+void mvf_conv2d_debug_buffer(float* p);
 
 #ifdef __cplusplus
 }

@@ -14,8 +14,15 @@ class F1Params(ctypes.Structure):
                 ("disp_range", ctypes.c_float), ("smooth_w", ctypes.c_float), ("flags", ctypes.c_int)]
 
 
+class Conv2dDesc(ctypes.Structure):
+    _fields_ = [("B", ctypes.c_int), ("Cin", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int),
+                ("Cout", ctypes.c_int), ("KH", ctypes.c_int), ("KW", ctypes.c_int), ("pad", ctypes.c_int),
+                ("stride", ctypes.c_int), ("x_stride", ctypes.c_longlong * 3), ("y_stride", ctypes.c_longlong * 3)]
+
+
 _vp, _sz, _i, _f = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float
 _P = ctypes.POINTER(F1Params)
+_CD = ctypes.POINTER(Conv2dDesc)
 
 # name -> (restype, argtypes); every symbol include/monovifi_b200.h declares
 SIGNATURES = {
@@ -38,6 +45,12 @@ SIGNATURES = {
     "mvf_smooth_loss_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mvf_si_log_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _sz, _f, _vp]),
     "mvf_si_log_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _sz, _f, _vp]),
+    "mvf_conv2d_packed_filter_floats": (_sz, [_i, _i, _i, _i]),
+    "mvf_conv2d_pack_filters": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "mvf_conv2d_supported": (_i, [_CD]),
+    "mvf_conv2d_forward": (_i, [_CD, _vp, _vp, _vp, _vp, _i, _vp]),
+    "mvf_selftest_umma": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mvf_conv2d_debug_buffer": (None, [_vp]),
     "mvf_selftest_division": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
 }
 

@@ -1,0 +1,145 @@
+"""Tensor-core convolutions (tcgen05 / TMEM / TMA implicit GEMM on NCHW fp32, TF32 inputs, fp32 accumulate).
+
+`conv2d(x, weight, bias, stride, padding)` is a torch.autograd.Function over the C ABI in
+include/monovifi_b200.h (mvf_conv2d_*).  Forward and the input gradient run the same kernel (the latter on
+grad_out with the flipped / transposed filter bank); the weight gradient has its own kernel.  `supported()`
+tells the dispatcher in conv.py which problems the kernels cover; nothing here falls back silently.
+Activations are NCHW-shaped tensors in torch.channels_last memory format (the kernels' TMA boxes need channels
+contiguous); tensors arriving in another layout are converted once on entry.
+"""
+import torch
+
+from . import _lib
+
+launches = {"fprop": 0, "dgrad": 0, "wgrad": 0, "pack": 0}
+
+
+def _desc(B, Cin, H, W, Cout, KH, KW, pad, stride, x, y):
+    d = _lib.Conv2dDesc(B, Cin, H, W, Cout, KH, KW, pad, stride)
+    for i, dim in enumerate((0, 2, 3)):  # batch, row, column strides; the channel stride is 1
+        d.x_stride[i] = x.stride(dim)
+        d.y_stride[i] = y.stride(dim)
+    return d
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _as_input(x):
+    """NCHW-shaped fp32 tensor in channels-last memory (unit channel stride, 16-byte aligned pixels): what the
+    TMA descriptor of the kernels needs.  Channel slices of a wider channels-last tensor qualify as they are."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    sB, sC, sH, sW = x.stride()
+    if (sC != 1 and x.shape[1] != 1) or sW % 4 or sH % 4 or sB % 4 or x.data_ptr() % 16:
+        x = x.contiguous(memory_format=torch.channels_last)
+        if x.stride(1) != 1:  # torch keeps NCHW strides for some degenerate shapes (C == 1 or H == W == 1)
+            B, C, H, W = x.shape
+            x = x.as_strided((B, C, H, W), (H * W * C, 1, W * C, C))
+    return x
+
+
+def out_hw(H, W, KH, KW, pad, stride):
+    return (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+
+
+def supported(x, weight, stride, padding, dilation=1, groups=1):
+    def pair(v):
+        return (v, v) if isinstance(v, int) else tuple(v)
+    if not x.is_cuda or x.dim() != 4 or groups != 1 or pair(dilation) != (1, 1):
+        return False
+    sh, sw = pair(stride)
+    ph, pw = pair(padding)
+    Cout, Cin, KH, KW = weight.shape
+    if sh != sw or sh not in (1, 2) or ph != pw or Cin % 4:
+        return False
+    return True
+
+
+def pack_filters(weight, dgrad=False):
+    Cout, Cin, KH, KW = weight.shape
+    N, K = (Cin, Cout) if dgrad else (Cout, Cin)
+    n = _lib.lib().mvf_conv2d_packed_filter_floats(N, K, KH, KW)
+    out = torch.empty(n, device=weight.device, dtype=torch.float32)
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    launches["pack"] += 1
+    _lib.check(_lib.lib().mvf_conv2d_pack_filters(w.data_ptr(), out.data_ptr(), Cout, Cin, KH, KW, 1 if dgrad else 0,
+                                                  _stream(weight)), "mvf_conv2d_pack_filters")
+    return out
+
+
+def conv_forward_raw(x, w_packed, bias, Cout, KH, KW, pad, stride=1, act=0, out=None):
+    """y = conv(x) with a packed filter bank; x and y are NCHW-shaped, channels-last in memory."""
+    x = _as_input(x)
+    B, Cin, H, W = x.shape
+    Ho, Wo = out_hw(H, W, KH, KW, pad, stride)
+    if out is None:
+        y = torch.empty(B, Ho, Wo, Cout, device=x.device, dtype=torch.float32).permute(0, 3, 1, 2)
+    else:
+        y = out
+        assert (y.stride(1) == 1 or Cout == 1) and tuple(y.shape) == (B, Cout, Ho, Wo)
+    d = _desc(B, Cin, H, W, Cout, KH, KW, pad, stride, x, y)
+    b = None if bias is None else bias.detach().float().contiguous()
+    rc = _lib.lib().mvf_conv2d_forward(d, x.data_ptr(), w_packed.data_ptr(), None if b is None else b.data_ptr(),
+                                       y.data_ptr(), act, _stream(x))
+    _lib.check(rc, "mvf_conv2d_forward")
+    return y
+
+
+class _Conv2dTC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, pad, stride):
+        Cout, Cin, KH, KW = weight.shape
+        launches["fprop"] += 1
+        x = _as_input(x)
+        y = conv_forward_raw(x, pack_filters(weight), bias, Cout, KH, KW, pad, stride)
+        ctx.save_for_backward(x, weight)
+        ctx.pad, ctx.stride, ctx.has_bias = pad, stride, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        Cout, Cin, KH, KW = weight.shape
+        pad, stride = ctx.pad, ctx.stride
+        gx = gw = gb = None
+        gy = _as_input(gy)
+        if ctx.needs_input_grad[0]:
+            if stride == 1 and Cout % 4 == 0 and pad <= KH - 1 and pad <= KW - 1:
+                launches["dgrad"] += 1
+                gx = conv_forward_raw(gy, pack_filters(weight, dgrad=True), None, Cin, KH, KW, KH - 1 - pad)
+            else:
+                gx = input_grad_library(x, gy, weight, pad, stride)
+        if ctx.needs_input_grad[1]:
+            gw = weight_grad(x, gy, weight.shape, pad, stride)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum((0, 2, 3))
+        return gx, gw, gb, None, None
+
+
+def input_grad_library(x, gy, weight, pad, stride):
+    """dL/dx of the shapes the tcgen05 dgrad does not cover yet (strided convolutions): cuDNN, counted in conv.stats."""
+    from . import conv
+    conv.stats["cudnn_dgrad"] = conv.stats.get("cudnn_dgrad", 0) + 1
+    gx, _, _ = torch.ops.aten.convolution_backward(gy, x, weight, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1,
+                                                   [True, False, False])
+    return gx
+
+
+def weight_grad(x, gy, wshape, pad, stride=1):
+    """dL/dw.  Until the tcgen05 wgrad kernel covers the shape this is cuDNN's (a library call, counted in conv.stats)."""
+    from . import conv
+    conv.stats["cudnn_wgrad"] = conv.stats.get("cudnn_wgrad", 0) + 1
+    w = torch.empty(wshape, device=x.device, dtype=x.dtype).contiguous(memory_format=torch.channels_last)
+    _, gw, _ = torch.ops.aten.convolution_backward(gy, x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1,
+                                                   [False, True, False])
+    return gw
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0):
+    pad = padding if isinstance(padding, int) else padding[0]
+    st = stride if isinstance(stride, int) else stride[0]
+    return _Conv2dTC.apply(x, weight, bias, pad, st)

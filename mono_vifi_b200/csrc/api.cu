@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 
+#include "conv_tc.cuh"
 #include "f1.cuh"
 #include "ops.cuh"
 
@@ -204,6 +205,49 @@ int mvf_si_log_bwd(const float* pred, const float* target, const float* mask, co
                    float* g_pred, float* g_target, int B, size_t HW, float beta, void* stream) {
     if (!pred || !target || !stats || B <= 0 || HW == 0) return fail(MVF_ERR_INVALID, "mvf_si_log_bwd: bad argument");
     MVF_RUN("mvf_si_log_bwd", mvf::si_log_bwd(pred, target, mask, stats, gout, g_pred, g_target, B, HW, beta, (cudaStream_t)stream));
+}
+
+
+/* ---- tensor-core convolutions ----------------------------------------------------------------------------- */
+size_t mvf_conv2d_packed_filter_floats(int N, int K, int KH, int KW) {
+    if (N <= 0 || K <= 0 || KH <= 0 || KW <= 0) return 0;
+    return mvf::tc::packed_filter_floats(N, K, KH, KW);
+}
+int mvf_conv2d_pack_filters(const float* w, float* packed, int Cout, int Cin, int KH, int KW, int dgrad, void* stream) {
+    if (!w || !packed || Cout <= 0 || Cin <= 0 || KH <= 0 || KW <= 0) return fail(MVF_ERR_INVALID, "mvf_conv2d_pack_filters: bad argument");
+    MVF_RUN("mvf_conv2d_pack_filters", mvf::tc::pack_filters(w, packed, Cout, Cin, KH, KW, dgrad, (cudaStream_t)stream));
+}
+static mvf::tc::ConvDesc to_desc(const mvf_conv2d_desc* d) {
+    mvf::tc::ConvDesc c;
+    c.B = d->B; c.Cin = d->Cin; c.H = d->H; c.W = d->W; c.Cout = d->Cout; c.KH = d->KH; c.KW = d->KW; c.pad = d->pad;
+    c.stride = d->stride;
+    c.x_sB = d->x_stride[0]; c.x_sH = d->x_stride[1]; c.x_sW = d->x_stride[2];
+    c.y_sB = d->y_stride[0]; c.y_sH = d->y_stride[1]; c.y_sW = d->y_stride[2];
+    return c;
+}
+int mvf_selftest_umma(const float* A, const float* B, float* D, int N, int K, int a_mn_major, void* stream) {
+    if (!A || !B || !D || N < 16 || N > 256 || N % 16 || K < 32 || K % 32) return fail(MVF_ERR_INVALID, "mvf_selftest_umma: bad argument");
+    MVF_RUN("mvf_selftest_umma", mvf::tc::umma_selftest(A, B, D, N, K, a_mn_major, (cudaStream_t)stream));
+}
+void mvf_conv2d_debug_buffer(float* p) { mvf::tc::set_debug_buffer(p); }
+int mvf_conv2d_supported(const mvf_conv2d_desc* d) {
+    if (!d) return 0;
+    const char* why = mvf::tc::conv_check(to_desc(d));
+    if (why) {
+        fail(MVF_ERR_INVALID, why);
+        return 0;
+    }
+    return 1;
+}
+int mvf_conv2d_forward(const mvf_conv2d_desc* d, const float* x, const float* w_packed, const float* bias, float* y,
+                       int act, void* stream) {
+    if (!d || !x || !w_packed || !y) return fail(MVF_ERR_INVALID, "mvf_conv2d_forward: null pointer");
+    const mvf::tc::ConvDesc c = to_desc(d);
+    const char* why = mvf::tc::conv_check(c);
+    if (why) return fail(MVF_ERR_INVALID, why);
+    cudaError_t e = mvf::tc::conv_forward(c, x, w_packed, bias, y, act, (cudaStream_t)stream, &why);
+    if (e != cudaSuccess) return why ? fail(MVF_ERR_CUDA, why) : fail(MVF_ERR_CUDA, "mvf_conv2d_forward launch", e);
+    return MVF_OK;
 }
 
 }  // extern "C"

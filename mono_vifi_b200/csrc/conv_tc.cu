@@ -1,0 +1,358 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05, TF32 inputs, fp32 accumulation in TMEM) on
+// channels-last fp32 activations (NCHW-shaped tensors in torch.channels_last memory format) -- no im2col buffer.
+//
+//   fprop :  y[b,oy,ox,co] = sum_{kh,kw,ci} x[b, oy*s+kh-pad, ox*s+kw-pad, ci] * w[co,ci,kh,kw]     (stride s = 1 or 2)
+//   dgrad :  (s = 1) the same kernel on grad_out with the flipped / transposed filter bank and pad' = k-1-pad
+//
+// GEMM view per CTA: D[128 pixels, N_TILE couts] += A[128 pixels, 32 channels] . B[32 channels, N_TILE] for each
+// (filter tap, 32-channel block).  The 128 pixels are a TW x TH patch of one image (TW * TH = 128, chosen per layer),
+// so the A operand of a tap is one TMA box of the input, shifted by (kh-pad, kw-pad) and traversed with the
+// convolution stride; pixels outside the image (zero padding) and channels past Cin are zero-filled by the TMA unit.
+// Both operands are K-major with the 128-byte swizzle (A: one row per pixel, B: one row per cout of the pre-packed
+// filter bank).  [Why channels-last: with NCHW the shifted box would start at a 4-byte offset in the contiguous
+// dimension, which TMA rejects (illegal instruction, measured), and MN-major TF32 operands need the 32-byte-unit
+// swizzle; profiles/r1_conv_bringup.md.]
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected thread), warps 2..5 =
+// epilogue (TMEM -> registers -> bias / activation -> 128-byte-per-thread NHWC stores).
+//
+// Replaces the cuDNN calls behind nn.Conv2d in the reference's networks (layers.py:131,146; monodepth2.py; posenet.py).
+#include "conv_tc.cuh"
+
+#include <cstdlib>
+#include <mutex>
+
+#include "tc_common.cuh"
+
+namespace mvf {
+namespace tc {
+
+namespace {
+
+constexpr int TILE_M = 128;                         // output pixels per CTA (= UMMA M)
+constexpr int BLOCK_K = 32, KGROUPS = BLOCK_K / 8;  // channels per pipeline stage, UMMA K = 8 (tf32)
+constexpr int A_STAGE_BYTES = TILE_M * BLOCK_K * 4; // 16 KB
+constexpr int NTHREADS = 192;
+
+template <int N_TILE>
+struct Cfg {
+    static constexpr int B_STAGE_BYTES = N_TILE * BLOCK_K * 4;
+    static constexpr int STAGES = (N_TILE >= 256) ? 4 : ((N_TILE >= 128) ? 3 : 4);
+    static constexpr int TMEM_COLS = N_TILE < 32 ? 32 : N_TILE;
+    static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+struct ConvArgs {
+    float* y;
+    const float* bias;
+    long long y_sB, y_sH, y_sW;  // output strides in elements (channel stride 1)
+    int Cout, Ho, Wo;
+    int KH, KW, pad, stride;
+    int tw_log2;                 // tile = (1 << tw_log2) x (128 >> tw_log2) output pixels
+    int tiles_x, tiles_y;
+    int n_cblk;                  // ceil(Cin / 32)
+    int act;                     // 0 none, 1 relu, 2 elu
+    float* dbg;                  // debug: raw copy of pipeline stage 0 (A then B) of CTA (0,0); null in production
+};
+
+template <int N_TILE>
+__global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                              const __grid_constant__ CUtensorMap mapB, const ConvArgs p) {
+    using C = Cfg<N_TILE>;
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte alignment: the 128B-swizzle atoms of TMA and UMMA are defined on absolute shared-memory address bits
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smA = smem;
+    unsigned char* smB = smem + C::STAGES * A_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smB + C::STAGES * C::B_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + C::STAGES;
+    uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x;
+    const int tx = m % p.tiles_x, ty = (m / p.tiles_x) % p.tiles_y, b = m / (p.tiles_x * p.tiles_y);
+    const int TW = 1 << p.tw_log2, TH = TILE_M >> p.tw_log2;
+    const int x0 = tx * TW, y0 = ty * TH, n0 = blockIdx.y * N_TILE;
+    const int n_iters = p.KH * p.KW * p.n_cblk;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, C::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int it = 0; it < n_iters; ++it) {
+                const int s = it % C::STAGES;
+                const uint32_t ph = (it / C::STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const int tap = it / p.n_cblk, cb = it - tap * p.n_cblk;
+                const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
+                // A: dims (c, x, y, b), box (32, TW, TH, 1) traversed with the conv stride -> smem [pixel][32 c]
+                tma_load_4d(smA + s * A_STAGE_BYTES, &mapA, &full_bar[s], cb * BLOCK_K, x0 * p.stride + kw - p.pad,
+                            y0 * p.stride + kh - p.pad, b);
+                // B: dims (k within block, cout, tap * n_cblk + cb), box (32, N_TILE, 1) -> smem [cout][32 k]
+                tma_load_3d(smB + s * C::B_STAGE_BYTES, &mapB, &full_bar[s], 0, n0, it);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(TILE_M, N_TILE, /*A K-major*/ 0, /*B K-major*/ 0);
+            for (int it = 0; it < n_iters; ++it) {
+                const int s = it % C::STAGES;
+                const uint32_t ph = (it / C::STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(smA + s * A_STAGE_BYTES), b_base = smem_u32(smB + s * C::B_STAGE_BYTES);
+#pragma unroll
+                for (int kg = 0; kg < KGROUPS; ++kg) {
+                    // K-major SW128: rows of 32 k (128 B), 8-row groups 1024 B apart (SBO); k-group kg starts 32 B in
+                    const uint64_t adesc = make_smem_desc(a_base + kg * 32, 16, 1024, SWZ_128B);
+                    const uint64_t bdesc = make_smem_desc(b_base + kg * 32, 16, 1024, SWZ_128B);
+                    umma_tf32(tmem_d, adesc, bdesc, idesc, (it > 0 || kg > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);  // frees the stage when these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own the TMEM lane quarter (warp % 4); one thread = one output pixel =====
+        const int q = warp & 3;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int mrow = q * 32 + lane;
+        const int oy = y0 + (mrow >> p.tw_log2), ox = x0 + (mrow & (TW - 1));
+        const bool pix_ok = (oy < p.Ho) && (ox < p.Wo);
+        float* ypix = p.y + (long long)b * p.y_sB + (long long)oy * p.y_sH + (long long)ox * p.y_sW;
+        const bool vec_ok = ((p.Cout & 3) == 0) && ((reinterpret_cast<uintptr_t>(ypix) & 15) == 0);
+        constexpr int CH = (N_TILE >= 32) ? 32 : 16;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N_TILE; c0 += CH) {
+            uint32_t r[CH];
+            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            if constexpr (CH == 32) tmem_ld32(taddr, r);
+            else tmem_ld16(taddr, r);
+            tmem_ld_wait();
+            if (!pix_ok) continue;
+            float v[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const int n = n0 + c0 + j;
+                float t = __uint_as_float(r[j]);
+                if (p.bias && n < p.Cout) t += __ldg(p.bias + n);
+                if (p.act == 1) t = fmaxf(t, 0.f);
+                else if (p.act == 2) t = t > 0.f ? t : expm1f(t);
+                v[j] = t;
+            }
+            if (vec_ok) {
+#pragma unroll
+                for (int j = 0; j < CH; j += 4)
+                    if (n0 + c0 + j < p.Cout)
+                        *reinterpret_cast<float4*>(ypix + n0 + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < CH; ++j)
+                    if (n0 + c0 + j < p.Cout) ypix[n0 + c0 + j] = v[j];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
+        const float* src = reinterpret_cast<const float*>(smA);
+        for (int i = threadIdx.x; i < A_STAGE_BYTES / 4; i += NTHREADS) p.dbg[i] = src[i];
+        src = reinterpret_cast<const float*>(smB);
+        for (int i = threadIdx.x; i < C::B_STAGE_BYTES / 4; i += NTHREADS) p.dbg[A_STAGE_BYTES / 4 + i] = src[i];
+        if (threadIdx.x == 0) p.dbg[A_STAGE_BYTES / 4 + C::B_STAGE_BYTES / 4] = __uint_as_float(tmem_d);
+    }
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_d, C::TMEM_COLS);
+    }
+}
+
+// ---- filter-bank packing -------------------------------------------------------------------------------------
+// fprop: Wp[tap][cb][co][kk] = w[co][cb*32+kk][kh][kw]                      (N = Cout, K = Cin)
+// dgrad: Wp[tap][cb][ci][kk] = w[cb*32+kk][ci][KH-1-kh][KW-1-kw]            (N = Cin,  K = Cout)
+__global__ void pack_filters_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int KH, int KW,
+                                    int dgrad) {
+    const int N = dgrad ? Cin : Cout, K = dgrad ? Cout : Cin;
+    const int ncb = (K + BLOCK_K - 1) / BLOCK_K;
+    const long long total = (long long)KH * KW * ncb * N * BLOCK_K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(i % BLOCK_K);
+        long long r = i / BLOCK_K;
+        const int n = (int)(r % N);
+        r /= N;
+        const int cb = (int)(r % ncb);
+        const int tap = (int)(r / ncb);
+        const int k = cb * BLOCK_K + kk;
+        int kh = tap / KW, kw = tap - kh * KW;
+        float v = 0.f;
+        if (k < K) {
+            if (dgrad) {
+                kh = KH - 1 - kh;
+                kw = KW - 1 - kw;
+                v = w[(((long long)k * Cin + n) * KH + kh) * KW + kw];
+            } else {
+                v = w[(((long long)n * Cin + k) * KH + kh) * KW + kw];
+            }
+        }
+        out[i] = v;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+template <int N_TILE>
+cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const ConvArgs& a, int B, cudaStream_t st) {
+    using C = Cfg<N_TILE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid(B * a.tiles_x * a.tiles_y, (a.Cout + N_TILE - 1) / N_TILE);
+    conv_igemm_kernel<N_TILE><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(mapA, mapB, a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t packed_filter_floats(int N, int K, int KH, int KW) {
+    return (size_t)KH * KW * ((K + BLOCK_K - 1) / BLOCK_K) * N * BLOCK_K;
+}
+
+cudaError_t pack_filters(const float* w, float* out, int Cout, int Cin, int KH, int KW, int dgrad, cudaStream_t st) {
+    const size_t total = packed_filter_floats(dgrad ? Cin : Cout, dgrad ? Cout : Cin, KH, KW);
+    const int threads = 256;
+    const int blocks = (int)((total + threads - 1) / threads < 1184 ? (total + threads - 1) / threads : 1184);
+    pack_filters_kernel<<<blocks, threads, 0, st>>>(w, out, Cout, Cin, KH, KW, dgrad);
+    return cudaGetLastError();
+}
+
+static int out_size(int n, int k, int pad, int stride) { return (n + 2 * pad - k) / stride + 1; }
+
+const char* conv_check(const ConvDesc& d) {
+    if (d.B <= 0 || d.Cin <= 0 || d.H <= 0 || d.W <= 0 || d.Cout <= 0 || d.KH <= 0 || d.KW <= 0) return "non-positive size";
+    if (d.stride != 1 && d.stride != 2) return "stride must be 1 or 2";
+    if (d.Cin % 4 != 0) return "input channels must be a multiple of 4 (TMA: 16-byte rows)";
+    if ((d.x_sH % 4) || (d.x_sW % 4) || (d.x_sB % 4)) return "input strides must be multiples of 4 elements (TMA: 16 bytes)";
+    if (d.pad < 0) return "negative padding";
+    if (d.H + 2 * d.pad < d.KH || d.W + 2 * d.pad < d.KW) return "empty output";
+    return nullptr;
+}
+
+static float* g_dbg = nullptr;
+void set_debug_buffer(float* p) { g_dbg = p; }
+
+cudaError_t conv_forward(const ConvDesc& d, const float* x, const float* w_packed, const float* bias, float* y, int act,
+                         cudaStream_t st, const char** why) {
+    *why = nullptr;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) {
+        *why = "cuTensorMapEncodeTiled is not available from the driver";
+        return cudaErrorNotSupported;
+    }
+    if (((uintptr_t)x & 15) || ((uintptr_t)w_packed & 15)) {
+        *why = "input / packed filter pointers must be 16-byte aligned";
+        return cudaErrorInvalidValue;
+    }
+    const int Ho = out_size(d.H, d.KH, d.pad, d.stride), Wo = out_size(d.W, d.KW, d.pad, d.stride);
+    ConvArgs a;
+    a.y = y;
+    a.bias = bias;
+    a.y_sB = d.y_sB; a.y_sH = d.y_sH; a.y_sW = d.y_sW;
+    a.Cout = d.Cout; a.Ho = Ho; a.Wo = Wo;
+    a.KH = d.KH; a.KW = d.KW; a.pad = d.pad; a.stride = d.stride;
+    // tile shape: the (2^j x 128/2^j) patch that covers the output with the least padding (ties: the widest)
+    int best = 5;
+    long long best_cost = -1;
+    for (int j = 7; j >= 1; --j) {
+        const int tw = 1 << j, th = TILE_M >> j;
+        const long long cost = (long long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = j;
+        }
+    }
+    a.tw_log2 = best;
+    const int TW = 1 << best, TH = TILE_M >> best;
+    a.tiles_x = (Wo + TW - 1) / TW;
+    a.tiles_y = (Ho + TH - 1) / TH;
+    a.n_cblk = (d.Cin + BLOCK_K - 1) / BLOCK_K;
+    a.act = act;
+    a.dbg = g_dbg;
+    int n_tile = 16;
+    while (n_tile < d.Cout && n_tile < 128) n_tile *= 2;
+
+    CUtensorMap mapA, mapB;
+    {   // input as (c, x, y, b); strides in bytes for dims 1..3; the box walks x and y with the convolution stride
+        cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)d.x_sW * 4, (cuuint64_t)d.x_sH * 4, (cuuint64_t)d.x_sB * 4};
+        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)(TW * d.stride), (cuuint32_t)(TH * d.stride), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
+        CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            *why = "cuTensorMapEncodeTiled failed for the input tensor";
+            return cudaErrorInvalidValue;
+        }
+    }
+    {   // packed filter bank as (32 k, Cout, taps * n_cblk)
+        cuuint64_t dims[3] = {BLOCK_K, (cuuint64_t)d.Cout, (cuuint64_t)(d.KH * d.KW * a.n_cblk)};
+        cuuint64_t strides[2] = {BLOCK_K * 4, (cuuint64_t)d.Cout * BLOCK_K * 4};
+        cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)n_tile, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w_packed), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            *why = "cuTensorMapEncodeTiled failed for the packed filter bank";
+            return cudaErrorInvalidValue;
+        }
+    }
+    switch (n_tile) {
+        case 16: return launch<16>(mapA, mapB, a, d.B, st);
+        case 32: return launch<32>(mapA, mapB, a, d.B, st);
+        case 64: return launch<64>(mapA, mapB, a, d.B, st);
+        default: return launch<128>(mapA, mapB, a, d.B, st);
+    }
+}
+
+}  // namespace tc
+}  // namespace mvf

@@ -1,0 +1,27 @@
+// Tensor-core (tcgen05 / TMEM / TMA) convolution kernels: host-side entry points.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace mvf {
+namespace tc {
+
+// convolution problem on channels-last tensors.  Input x[b][y][x][c] with element strides (x_sB, x_sH, x_sW, 1);
+// output y[b][oy][ox][co] with strides (y_sB, y_sH, y_sW, 1), Ho = (H + 2 pad - KH) / stride + 1.
+struct ConvDesc {
+    int B, Cin, H, W;
+    int Cout, KH, KW, pad, stride;
+    long long x_sB, x_sH, x_sW;
+    long long y_sB, y_sH, y_sW;
+};
+
+size_t packed_filter_floats(int N, int K, int KH, int KW);
+cudaError_t pack_filters(const float* w, float* out, int Cout, int Cin, int KH, int KW, int dgrad, cudaStream_t st);
+cudaError_t umma_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn_major, cudaStream_t st);
+void set_debug_buffer(float* p);  // development aid: dump of pipeline stage 0, see conv_tc.cu
+const char* conv_check(const ConvDesc& d);  // nullptr if the tcgen05 path covers the problem, else the reason
+cudaError_t conv_forward(const ConvDesc& d, const float* x, const float* w_packed, const float* bias, float* y, int act,
+                         cudaStream_t st, const char** why);
+
+}  // namespace tc
+}  // namespace mvf

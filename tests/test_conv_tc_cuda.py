@@ -1,0 +1,116 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolutions (through the C ABI) against torch's fp32 convolution
+(TF32 disabled: a true-fp32 reference).  TF32 rounds each input to 10 mantissa bits, so the tolerance is
+2e-3 of the output's magnitude (north_star: depth tensors within 1e-3 relative after the whole network)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, w, b, pad, stride=1):
+    import torch.nn.functional as F
+    return F.conv2d(x.double(), w.double(), None if b is None else b.double(), stride, pad).float()
+
+
+CASES = [
+    # B, Cin, H, W, Cout, k, pad, stride, bias
+    (1, 8, 4, 32, 16, 1, 0, 1, False),      # one tile, a quarter-full stage (zero-filled channels)
+    (1, 32, 4, 32, 16, 1, 0, 1, False),     # one full stage
+    (1, 64, 8, 64, 32, 1, 0, 1, True),      # several tiles and stages
+    (2, 64, 12, 40, 64, 3, 1, 1, True),     # 3x3 zero padding, ragged tile edges
+    (2, 16, 9, 37, 16, 3, 1, 1, False),     # odd width, Cin 16
+    (1, 96, 16, 64, 32, 3, 1, 1, True),     # Cin not a power of two
+    (2, 128, 24, 80, 128, 3, 1, 1, False),  # ResNet layer2 shape
+    (1, 256, 12, 40, 256, 3, 1, 1, False),  # two N tiles
+    (2, 512, 6, 20, 512, 3, 1, 1, False),   # ResNet layer4 shape: four N tiles, 144 pipeline iterations
+    (1, 64, 10, 36, 64, 3, 0, 1, True),     # valid convolution (reflection-padded input comes this way)
+    (1, 64, 8, 32, 24, 3, 2, 1, False),     # "full" padding = what dgrad of a pad-0 conv uses; Cout not a multiple of 16
+    (2, 16, 16, 64, 1, 3, 1, 1, True),      # dispconv: a single output channel
+    (2, 64, 24, 80, 128, 3, 1, 2, False),   # stride 2 (ResNet layer2.0.conv1)
+    (2, 64, 24, 80, 128, 1, 0, 2, False),   # 1x1 stride 2 (downsample)
+    (1, 8, 33, 71, 64, 7, 3, 2, False),     # 7x7 stride 2 stem on odd sizes (image channels padded 3 -> 8)
+    (1, 4, 16, 32, 16, 3, 1, 1, False),     # four input channels (16-byte pixels)
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_forward_vs_fp32(case):
+    import torch
+    from mono_vifi_b200 import conv_tc
+    B, Cin, H, W, Cout, k, pad, stride, bias = case
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g) if bias else None
+    assert conv_tc.supported(x, w, stride, pad)
+    y = conv_tc.conv_forward_raw(x, conv_tc.pack_filters(w), b, Cout, k, k, pad, stride)
+    torch.cuda.synchronize()
+    ref = _ref(x, w, b, pad, stride)
+    assert y.shape == ref.shape
+    err = (y - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
+def test_strided_input_and_output_views():
+    """channel slices of a wider tensor (what torch.cat would otherwise copy) and a channel-offset output"""
+    import torch
+    from mono_vifi_b200 import conv_tc
+    g = torch.Generator(device="cuda").manual_seed(6)
+    big = torch.randn(2, 96, 12, 64, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    x = big[:, 32:96]
+    w = torch.randn(32, 64, 3, 3, device="cuda", generator=g) / 24.0
+    out = torch.zeros(2, 48, 12, 64, device="cuda").contiguous(memory_format=torch.channels_last)
+    conv_tc.conv_forward_raw(x, conv_tc.pack_filters(w), None, 32, 3, 3, 1, out=out[:, 16:48])
+    ref = _ref(x.contiguous(), w, None, 1)
+    assert (out[:, 16:48] - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    assert out[:, :16].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("case", [(2, 64, 12, 40, 64, 3, 1, 1), (1, 32, 8, 64, 16, 3, 1, 1), (2, 64, 10, 36, 32, 3, 0, 1),
+                                  (1, 128, 6, 20, 64, 1, 0, 1), (2, 64, 12, 40, 128, 3, 1, 2), (1, 16, 9, 33, 1, 3, 1, 1)])
+def test_autograd_vs_fp32(case):
+    import torch
+    from mono_vifi_b200 import conv_tc
+    B, Cin, H, W, Cout, k, pad, stride = case
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g, requires_grad=True)
+    w = (torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5).requires_grad_(True)
+    b = torch.randn(Cout, device="cuda", generator=g, requires_grad=True)
+    y = conv_tc.conv2d(x, w, b, stride, pad)
+    gy = torch.randn(y.shape, device="cuda", generator=g)
+    y.backward(gy)
+    xr, wr, br = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    yr = torch.nn.functional.conv2d(xr, wr, br, stride, pad)
+    yr.backward(gy.double())
+    for got, ref in ((x.grad, xr.grad), (w.grad, wr.grad), (b.grad, br.grad)):
+        ref = ref.float()
+        assert (got - ref).abs().max().item() <= 3e-3 * ref.abs().max().item()
+
+
+def test_unsupported_shapes_are_reported():
+    import torch
+    from mono_vifi_b200 import _lib, conv_tc
+    x = torch.randn(1, 3, 8, 32, device="cuda")
+    w = torch.randn(8, 3, 3, 3, device="cuda")
+    assert not conv_tc.supported(x, w, 1, 1)           # Cin % 4
+    assert not conv_tc.supported(torch.randn(1, 8, 8, 32, device="cuda"), torch.randn(8, 8, 3, 3, device="cuda"), 3, 1)
+    d = _lib.Conv2dDesc(1, 3, 8, 32, 8, 3, 3, 1, 1)
+    assert _lib.lib().mvf_conv2d_supported(d) == 0 and b"multiple of 4" in _lib.lib().mvf_last_error()
+
+
+def test_umma_selftest_pins_descriptors():
+    """D = A . B^T on one CTA for both operand layouts the kernels use (K-major; MN-major with the 32-byte-unit swizzle)"""
+    import torch
+    from mono_vifi_b200 import _lib
+    L = _lib.lib()
+    for mn in (0, 1):
+        for N, K in ((16, 32), (64, 64), (256, 96)):
+            g = torch.Generator(device="cuda").manual_seed(1)
+            A = torch.randn(128, K, device="cuda", generator=g)
+            Bm = torch.randn(N, K, device="cuda", generator=g)
+            D = torch.full((128, N), -5.0, device="cuda")
+            Ain = A.t().contiguous() if mn else A
+            _lib.check(L.mvf_selftest_umma(Ain.data_ptr(), Bm.data_ptr(), D.data_ptr(), N, K, mn,
+                                           torch.cuda.current_stream().cuda_stream), "mvf_selftest_umma")
+            ref = A.double() @ Bm.double().t()
+            assert (D.double() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() * (K / 32) ** 0.5
