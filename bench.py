@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--cpu-batch", type=int, default=2, help="bounded CPU sample: images per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--conv-backend", default=os.environ.get("MVF_CONV_BACKEND", "cudnn"))
+    ap.add_argument("--conv-backend", default=os.environ.get("MVF_CONV_BACKEND", "tcgen05"), choices=["tcgen05", "cudnn"])
     return ap.parse_args()
 
 
@@ -195,7 +195,7 @@ class ClockSampler:
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from mono_vifi_b200 import _lib, conv, ddp, fused, trainer as TR
+    from mono_vifi_b200 import _lib, conv, conv_tc, ddp, fused, trainer as TR
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (our arm) needs a CUDA device: there is no CPU fallback")
@@ -227,6 +227,9 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     fused.timing = []
     l0 = dict(fused.launches)
+    c0 = dict(conv_tc.launches)
+    for k in conv.stats:
+        conv.stats[k] = 0
     barrier()
     if sampler:
         sampler.start()
@@ -242,7 +245,9 @@ def run_ours(args):
     for tag, a, b in fused.timing:
         kt[tag].append(a.elapsed_time(b))
     fused.timing = None
-    my_launches = sum(fused.launches[k] - l0[k] for k in l0) + 0
+    conv_launches = {k: conv_tc.launches[k] - c0[k] for k in c0}
+    conv_calls = dict(conv.stats)
+    my_launches = sum(fused.launches[k] - l0[k] for k in l0) + sum(conv_launches.values())
     # ---- timed region 2: end to end from pinned host memory -----------------------------------------------------
     stage = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
     barrier()
@@ -287,7 +292,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32 (tf32 tensor-core convolutions, as torch's cuDNN default)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": args.batch, "global_batch": args.batch * world,
                        "height": args.height, "width": args.width, "parallelism": "dp%d" % world,
-                       "conv_backend": conv.get_backend(), "conv_calls": dict(conv.stats),
+                       "conv_backend": conv.get_backend(), "conv_calls_timed_region": conv_calls,
+                       "conv_kernel_launches_timed_region": conv_launches,
                        "l2": "working set (activations, several GB) is far larger than the 126 MB L2; inputs rotate between two batches"},
             "e2e": {"value": args.batch * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},

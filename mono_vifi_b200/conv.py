@@ -3,12 +3,13 @@
 `Conv2d` keeps nn.Conv2d's parameters / state_dict keys (`weight`, `bias`), so checkpoints of the reference load
 unchanged, and routes the arithmetic through `conv2d()`:
 
-  backend "tcgen05"  hand-written sm_100a implicit-GEMM kernels (mono_vifi_b200/csrc/conv_*.cu) for the shapes
-                     they cover (see `tcgen05_supported`);
-  backend "cudnn"    torch's F.conv2d (cuDNN, a LIBRARY baseline -- what the reference itself runs on).
+  backend "tcgen05"  hand-written sm_100a implicit-GEMM kernels (mono_vifi_b200/csrc/conv_tc.cu, conv_wgrad.cu) on
+                     channels-last activations -- the default on a CUDA device;
+  backend "cudnn"    torch's F.conv2d (cuDNN, a LIBRARY baseline -- what the reference itself runs on), kept for
+                     A/B timing (MVF_CONV_BACKEND=cudnn) and for CPU tensors (the host-side tests).
 
-Select with set_backend() or MVF_CONV_BACKEND.  Shapes the tcgen05 kernels do not cover yet fall through to
-cuDNN and are counted in `stats` so the bench can report how much of the conv work ran on which path.
+Every call is counted in `stats` so the bench can report how much of the conv work ran on which path; shapes the
+tcgen05 kernels do not cover are routed to cuDNN and show up there -- never silently.
 """
 import os
 
@@ -16,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-_backend = os.environ.get("MVF_CONV_BACKEND", "cudnn")
+_backend = os.environ.get("MVF_CONV_BACKEND", "tcgen05")
 stats = {"tcgen05": 0, "cudnn": 0}
 
 
@@ -32,8 +33,14 @@ def get_backend():
 
 
 def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
-    if _backend == "tcgen05":
+    if _backend == "tcgen05" and x.is_cuda:
         from . import conv_tc
+        cin = weight.shape[1]
+        if cin % 4:
+            # image-like inputs (3 or 6 channels): zero channels up to a 16-byte pixel; autograd slices the gradient back
+            extra = 4 - cin % 4
+            x = F.pad(x, (0, 0, 0, 0, 0, extra))
+            weight = F.pad(weight, (0, 0, 0, 0, 0, extra))
         if conv_tc.supported(x, weight, stride, padding, dilation, groups):
             stats["tcgen05"] += 1
             return conv_tc.conv2d(x, weight, bias, stride, padding)
