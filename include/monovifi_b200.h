@@ -144,6 +144,16 @@ int mvf_conv2d_supported(const mvf_conv2d_desc* d); /* 1 / 0 (reason in mvf_last
 int mvf_conv2d_forward(const mvf_conv2d_desc* d, const float* x, const float* w_packed, const float* bias /*or NULL*/,
                        float* y, int act, void* stream);
 
+/* weight gradient: grad_w[Cout,Cin,KH,KW] (contiguous, the parameter's layout) = sum over output pixels of
+ * grad_out (x) input patches; d->x_stride describes x, d->y_stride describes grad_out (both channels-last).
+ * Split-K partial sums go to `workspace` (mvf_conv2d_wgrad_workspace_floats(d) floats, caller-owned scratch) and are
+ * added in a fixed order: results are bitwise reproducible.  Constraints (mvf_conv2d_wgrad_supported): at most 9
+ * taps, channel counts % 4 == 0, Cout <= 32 or Cout % 32 == 0, stride 1 or 2. */
+int mvf_conv2d_wgrad_supported(const mvf_conv2d_desc* d);
+size_t mvf_conv2d_wgrad_workspace_floats(const mvf_conv2d_desc* d);
+int mvf_conv2d_wgrad(const mvf_conv2d_desc* d, const float* x, const float* grad_out, float* grad_w, float* workspace,
+                     size_t workspace_floats, void* stream);
+
 /* device self-test: q_sequence[i] = the kernels' shared-reciprocal division of a[i] by b[i], q_ieee[i] = the
  * IEEE quotient (div.rn.f32); the two must be bit-identical for operands in the normal range. */
 int mvf_selftest_division(const float* a, const float* b, float* q_sequence, float* q_ieee, size_t n, void* stream);

@@ -49,6 +49,9 @@ SIGNATURES = {
     "mvf_conv2d_pack_filters": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mvf_conv2d_supported": (_i, [_CD]),
     "mvf_conv2d_forward": (_i, [_CD, _vp, _vp, _vp, _vp, _i, _vp]),
+    "mvf_conv2d_wgrad_supported": (_i, [_CD]),
+    "mvf_conv2d_wgrad_workspace_floats": (_sz, [_CD]),
+    "mvf_conv2d_wgrad": (_i, [_CD, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mvf_selftest_umma": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "mvf_conv2d_debug_buffer": (None, [_vp]),
     "mvf_selftest_division": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),

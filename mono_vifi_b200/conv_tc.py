@@ -129,8 +129,31 @@ def input_grad_library(x, gy, weight, pad, stride):
     return gx
 
 
+_wgrad_ws = {}
+
+
 def weight_grad(x, gy, wshape, pad, stride=1):
-    """dL/dw.  Until the tcgen05 wgrad kernel covers the shape this is cuDNN's (a library call, counted in conv.stats)."""
+    """dL/dw on the tcgen05 wgrad kernel; shapes it does not cover (7x7 stem, odd channel counts) go to cuDNN and
+    are counted in conv.stats -- never silently."""
+    Cout, Cin, KH, KW = wshape
+    B, _, H, W = x.shape
+    gy = _as_input(gy)
+    if Cout == 1 and gy.stride(3) != 1:
+        gy = gy.contiguous()
+    d = _desc(B, Cin, H, W, Cout, KH, KW, pad, stride, x, gy)
+    L = _lib.lib()
+    if Cout % 4 == 0 and L.mvf_conv2d_wgrad_supported(d):
+        n = L.mvf_conv2d_wgrad_workspace_floats(d)
+        key = (x.device.index, _stream(x))
+        ws = _wgrad_ws.get(key)
+        if ws is None or ws.numel() < n:
+            ws = torch.empty(max(n, 1 << 20), device=x.device, dtype=torch.float32)
+            _wgrad_ws[key] = ws
+        gw = torch.empty(Cout, Cin, KH, KW, device=x.device, dtype=torch.float32)
+        launches["wgrad"] += 1
+        _lib.check(L.mvf_conv2d_wgrad(d, x.data_ptr(), gy.data_ptr(), gw.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x)),
+                   "mvf_conv2d_wgrad")
+        return gw
     from . import conv
     conv.stats["cudnn_wgrad"] = conv.stats.get("cudnn_wgrad", 0) + 1
     w = torch.empty(wshape, device=x.device, dtype=x.dtype).contiguous(memory_format=torch.channels_last)

@@ -249,5 +249,37 @@ int mvf_conv2d_forward(const mvf_conv2d_desc* d, const float* x, const float* w_
     if (e != cudaSuccess) return why ? fail(MVF_ERR_CUDA, why) : fail(MVF_ERR_CUDA, "mvf_conv2d_forward launch", e);
     return MVF_OK;
 }
+static mvf::tc::WgradDesc to_wdesc(const mvf_conv2d_desc* d) {
+    mvf::tc::WgradDesc c;
+    c.B = d->B; c.Cin = d->Cin; c.H = d->H; c.W = d->W; c.Cout = d->Cout; c.KH = d->KH; c.KW = d->KW; c.pad = d->pad;
+    c.stride = d->stride;
+    c.x_sB = d->x_stride[0]; c.x_sH = d->x_stride[1]; c.x_sW = d->x_stride[2];
+    c.g_sB = d->y_stride[0]; c.g_sH = d->y_stride[1]; c.g_sW = d->y_stride[2];
+    return c;
+}
+int mvf_conv2d_wgrad_supported(const mvf_conv2d_desc* d) {
+    if (!d) return 0;
+    const char* why = mvf::tc::wgrad_check(to_wdesc(d));
+    if (why) {
+        fail(MVF_ERR_INVALID, why);
+        return 0;
+    }
+    return 1;
+}
+size_t mvf_conv2d_wgrad_workspace_floats(const mvf_conv2d_desc* d) {
+    if (!d || mvf::tc::wgrad_check(to_wdesc(d))) return 0;
+    return mvf::tc::wgrad_workspace_floats(to_wdesc(d));
+}
+int mvf_conv2d_wgrad(const mvf_conv2d_desc* d, const float* x, const float* grad_out, float* grad_w, float* workspace,
+                     size_t workspace_floats, void* stream) {
+    if (!d || !x || !grad_out || !grad_w || !workspace) return fail(MVF_ERR_INVALID, "mvf_conv2d_wgrad: null pointer");
+    const mvf::tc::WgradDesc c = to_wdesc(d);
+    const char* why = mvf::tc::wgrad_check(c);
+    if (why) return fail(MVF_ERR_INVALID, why);
+    if (workspace_floats < mvf::tc::wgrad_workspace_floats(c)) return fail(MVF_ERR_WORKSPACE, "mvf_conv2d_wgrad: workspace too small");
+    cudaError_t e = mvf::tc::conv_wgrad(c, x, grad_out, grad_w, workspace, (cudaStream_t)stream, &why);
+    if (e != cudaSuccess) return why ? fail(MVF_ERR_CUDA, why) : fail(MVF_ERR_CUDA, "mvf_conv2d_wgrad launch", e);
+    return MVF_OK;
+}
 
 }  // extern "C"

@@ -15,6 +15,18 @@ struct ConvDesc {
     long long y_sB, y_sH, y_sW;
 };
 
+// wgrad problem on channels-last tensors: dw[Cout,Cin,KH,KW] = sum_pixels gy . x  (conv_wgrad.cu)
+struct WgradDesc {
+    int B, Cin, H, W;
+    int Cout, KH, KW, pad, stride;
+    long long x_sB, x_sH, x_sW;
+    long long g_sB, g_sH, g_sW;
+};
+const char* wgrad_check(const WgradDesc& d);
+size_t wgrad_workspace_floats(const WgradDesc& d);
+cudaError_t conv_wgrad(const WgradDesc& d, const float* x, const float* gy, float* dw, float* workspace, cudaStream_t st,
+                       const char** why);
+
 size_t packed_filter_floats(int N, int K, int KH, int KW);
 cudaError_t pack_filters(const float* w, float* out, int Cout, int Cin, int KH, int KW, int dgrad, cudaStream_t st);
 cudaError_t umma_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn_major, cudaStream_t st);

@@ -114,3 +114,42 @@ def test_umma_selftest_pins_descriptors():
                                            torch.cuda.current_stream().cuda_stream), "mvf_selftest_umma")
             ref = A.double() @ Bm.double().t()
             assert (D.double() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() * (K / 32) ** 0.5
+
+
+WGRAD_CASES = [
+    # B, Cin, H, W, Cout, k, pad, stride
+    (1, 32, 4, 32, 32, 1, 0, 1),      # one patch per image row group, one tap
+    (2, 64, 12, 40, 64, 3, 1, 1),     # 3x3, ragged patches
+    (2, 16, 16, 64, 16, 3, 1, 1),     # narrow channels (zero-filled cout / cin blocks)
+    (1, 96, 16, 64, 32, 3, 1, 1),     # three cin tiles
+    (2, 128, 24, 80, 128, 3, 1, 1),   # ResNet layer2
+    (2, 512, 6, 20, 512, 3, 1, 1),    # ResNet layer4: 4 x 16 tiles, few pixels
+    (2, 64, 24, 80, 128, 3, 1, 2),    # stride 2
+    (2, 64, 24, 80, 128, 1, 0, 2),    # 1x1 stride 2 (downsample)
+    (2, 64, 10, 36, 32, 3, 0, 1),     # valid convolution
+    (3, 256, 6, 20, 12, 1, 0, 1),     # pose head: 12 output channels
+    (12, 64, 48, 160, 64, 3, 1, 1),   # ResNet layer1 at the benchmark size (split-K over 148 CTAs)
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_wgrad_vs_fp64(case):
+    import torch
+    from mono_vifi_b200 import conv_tc
+    B, Cin, H, W, Cout, k, pad, stride = case
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    Ho, Wo = conv_tc.out_hw(H, W, k, k, pad, stride)
+    gy = torch.randn(B, Cout, Ho, Wo, device="cuda", generator=g)
+    before = dict(conv_tc.launches)
+    gw = conv_tc.weight_grad(conv_tc._as_input(x), gy, (Cout, Cin, k, k), pad, stride)
+    torch.cuda.synchronize()
+    assert conv_tc.launches["wgrad"] == before["wgrad"] + 1, "the tcgen05 wgrad kernel must cover this shape"
+    wr = torch.zeros(Cout, Cin, k, k, device="cuda", dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.conv2d(x.double(), wr, None, stride, pad).backward(gy.double())
+    ref = wr.grad.float()
+    err = (gw - ref).abs().max().item()
+    assert err <= 3e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
+    # bitwise reproducible (fixed-order split-K reduction)
+    gw2 = conv_tc.weight_grad(conv_tc._as_input(x), gy, (Cout, Cin, k, k), pad, stride)
+    assert torch.equal(gw, gw2)
