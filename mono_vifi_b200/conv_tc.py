@@ -12,6 +12,21 @@ import torch
 from . import _lib
 
 launches = {"fprop": 0, "dgrad": 0, "wgrad": 0, "pack": 0}
+# when `timing` is a list, every tensor-core launch is bracketed by CUDA events on the launching stream and recorded
+# as (tag, algorithmic flops, start, end) -- bench.py derives the achieved TFLOP/s of the conv kernels from it
+timing = None
+_tag = "fprop"
+
+
+def _timed(tag, flops, fn):
+    if timing is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    timing.append((tag, flops, e0, e1))
+    return r
 
 
 def _desc(B, Cin, H, W, Cout, KH, KW, pad, stride, x, y):
@@ -83,8 +98,9 @@ def conv_forward_raw(x, w_packed, bias, Cout, KH, KW, pad, stride=1, act=0, out=
         assert (y.stride(1) == 1 or Cout == 1) and tuple(y.shape) == (B, Cout, Ho, Wo)
     d = _desc(B, Cin, H, W, Cout, KH, KW, pad, stride, x, y)
     b = None if bias is None else bias.detach().float().contiguous()
-    rc = _lib.lib().mvf_conv2d_forward(d, x.data_ptr(), w_packed.data_ptr(), None if b is None else b.data_ptr(),
-                                       y.data_ptr(), act, _stream(x))
+    flops = 2.0 * B * Ho * Wo * Cout * Cin * KH * KW
+    rc = _timed(_tag, flops, lambda: _lib.lib().mvf_conv2d_forward(
+        d, x.data_ptr(), w_packed.data_ptr(), None if b is None else b.data_ptr(), y.data_ptr(), act, _stream(x)))
     _lib.check(rc, "mvf_conv2d_forward")
     return y
 
@@ -109,8 +125,13 @@ class _Conv2dTC(torch.autograd.Function):
         gy = _as_input(gy)
         if ctx.needs_input_grad[0]:
             if stride == 1 and Cout % 4 == 0 and pad <= KH - 1 and pad <= KW - 1:
+                global _tag
                 launches["dgrad"] += 1
-                gx = conv_forward_raw(gy, pack_filters(weight, dgrad=True), None, Cin, KH, KW, KH - 1 - pad)
+                _tag = "dgrad"
+                try:
+                    gx = conv_forward_raw(gy, pack_filters(weight, dgrad=True), None, Cin, KH, KW, KH - 1 - pad)
+                finally:
+                    _tag = "fprop"
             else:
                 gx = input_grad_library(x, gy, weight, pad, stride)
         if ctx.needs_input_grad[1]:
@@ -151,8 +172,10 @@ def weight_grad(x, gy, wshape, pad, stride=1):
             _wgrad_ws[key] = ws
         gw = torch.empty(Cout, Cin, KH, KW, device=x.device, dtype=torch.float32)
         launches["wgrad"] += 1
-        _lib.check(L.mvf_conv2d_wgrad(d, x.data_ptr(), gy.data_ptr(), gw.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x)),
-                   "mvf_conv2d_wgrad")
+        Ho, Wo = out_hw(H, W, KH, KW, pad, stride)
+        flops = 2.0 * B * Ho * Wo * Cout * Cin * KH * KW
+        _lib.check(_timed("wgrad", flops, lambda: L.mvf_conv2d_wgrad(d, x.data_ptr(), gy.data_ptr(), gw.data_ptr(), ws.data_ptr(),
+                                                                      ws.numel(), _stream(x))), "mvf_conv2d_wgrad")
         return gw
     from . import conv
     conv.stats["cudnn_wgrad"] = conv.stats.get("cudnn_wgrad", 0) + 1

@@ -79,13 +79,19 @@ def single_frame_losses(models, inputs, opt):
 class TrainStep:
     """zero_grad -> forward -> backward -> (all-reduce) -> clip -> AdamW  (train.py:656-666)."""
 
-    def __init__(self, opt, device, models=None, distributed=False):
+    def __init__(self, opt, device, models=None, distributed=False, capturable=False):
         self.opt, self.device = opt, device
         self.models = models if models is not None else build_models(opt, device)
         # the reference appends every model's parameters (train.py:198-200)
         self.params = [p for m in self.models.values() for p in m.parameters()]
-        self.optimizer = torch.optim.AdamW(self.params, lr=opt.learning_rate, weight_decay=opt.weight_decay)
+        # capturable: step counters live on the device so that the whole step can be recorded into a CUDA graph
+        self.optimizer = torch.optim.AdamW(self.params, lr=opt.learning_rate, weight_decay=opt.weight_decay,
+                                           capturable=bool(capturable and device.type == "cuda"))
         self.reducer = FlatGradAllReduce(self.params) if distributed else None
+        # All training work runs on one dedicated (non-default) stream.  autograd binds each parameter's gradient
+        # accumulator to the stream of its first use; binding them to the legacy default stream would make the step
+        # impossible to record into a CUDA graph later (GraphedTrainStep).
+        self.stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
 
     def train(self):
         for m in self.models.values():
@@ -102,12 +108,64 @@ class TrainStep:
             self.reducer.allreduce_mean()
         return out
 
-    def __call__(self, inputs):
+    def _step(self, inputs):
         out = self.forward_backward(inputs)
         if self.opt.clip_grad is not None and self.opt.clip_grad > 0:
             torch.nn.utils.clip_grad_norm_([p for p in self.params if p.grad is not None], self.opt.clip_grad)
         self.optimizer.step()
-        return out["loss"].detach()
+        loss = out["loss"].detach()
+        for m in self.models.values():  # the reference's modules keep their last activations; drop the graph they hold
+            if hasattr(m, "features"):
+                m.features = None
+            if hasattr(m, "outputs"):
+                m.outputs = None
+        return loss
+
+    def __call__(self, inputs):
+        if self.stream is None:
+            return self._step(inputs)
+        cur = torch.cuda.current_stream(self.device)
+        if cur == self.stream:
+            return self._step(inputs)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            loss = self._step(inputs)
+        cur.wait_stream(self.stream)
+        return loss
+
+
+class GraphedTrainStep:
+    """The whole optimisation step (zero_grad -> forward -> backward -> all-reduce -> clip -> AdamW) recorded once into
+    a CUDA graph and replayed: one graph launch per step instead of several thousand kernel launches, so the GPU is
+    never waiting for the host.  Inputs are copied into static device buffers before each replay (shapes are fixed, as
+    they are in the reference's training loop: drop_last=True, train.py:110-117)."""
+
+    def __init__(self, step, example_inputs, warmup=3):
+        self.step = step
+        dev = step.device
+        self.static_inputs = {k: v.to(dev).clone() for k, v in example_inputs.items()}
+        self.stream = step.stream
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.stream):
+            for _ in range(warmup):  # eager: lazy initialisations (workspaces, function attributes, used-parameter map)
+                step(self.static_inputs)
+        torch.cuda.current_stream(dev).wait_stream(self.stream)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        if step.reducer is None:
+            step.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self.static_loss = step(self.static_inputs)
+
+    def load(self, inputs):
+        for k, v in inputs.items():
+            self.static_inputs[k].copy_(v, non_blocking=True)
+
+    def __call__(self, inputs=None):
+        if inputs is not None:
+            self.load(inputs)
+        self.graph.replay()  # launched on the caller's current stream; the static buffers order it after load()
+        return self.static_loss
 
 
 def synthetic_inputs(opt, device=None, seed=1234, pin=False):
