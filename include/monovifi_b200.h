@@ -158,10 +158,13 @@ int mvf_conv2d_wgrad(const mvf_conv2d_desc* d, const float* x, const float* grad
  * IEEE quotient (div.rn.f32); the two must be bit-identical for operands in the normal range. */
 int mvf_selftest_division(const float* a, const float* b, float* q_sequence, float* q_ieee, size_t n, void* stream);
 
-/* device self-test of the tcgen05 plumbing: D[128,N] = A . B^T on one CTA (TF32 in, fp32 out).  A is [128][K]
- * (a_mn_major = 0) or [K][128] (a_mn_major = 1, the layout NCHW activations have); B is [N][K].
+/* device self-test of the tcgen05 plumbing: D[128,N] = A . B^T on one CTA (TF32 in, fp32 out).  A is [160][K] (first 128 rows used;
+ * a_mn_major = 0) or [K][128] (a_mn_major = 1, the layout NCHW activations have); B is [N][K].
  * K % 32 == 0, N % 16 == 0, 16 <= N <= 256. */
 int mvf_selftest_umma(const float* A, const float* B, float* D, int N, int K, int a_mn_major, void* stream);
+/* same, K-major A given as [160][K]: D = A[row_off : row_off+128] . B^T, i.e. an operand whose start address is not
+ * aligned to the 1024-byte swizzle pattern (base_off_mode 1 sets the descriptor's base-offset field, 0 leaves it 0). */
+int mvf_selftest_umma_rows(const float* A, const float* B, float* D, int N, int K, int row_off, int base_off_mode, void* stream);
 /* development aid: when non-NULL, CTA (0,0) of mvf_conv2d_forward dumps its pipeline stage 0 there */
 void mvf_conv2d_debug_buffer(float* p);
 

@@ -47,7 +47,7 @@ def build(force=False, verbose=False, defines=(), out=None):
             raise RuntimeError("nvcc failed on %s" % s)
     # cudart (and, for the conv kernels' tensor maps, the driver API) are linked dynamically
     subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + objs +
-                          ["-lcudart", "-lcuda"])
+                          ["-lcudart"])
     return SO
 
 
@@ -68,7 +68,7 @@ def _build_variant(defines, out, verbose):
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % s)
     subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs +
-                          ["-lcudart", "-lcuda"])
+                          ["-lcudart"])
     return out
 
 

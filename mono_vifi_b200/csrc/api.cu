@@ -229,6 +229,11 @@ int mvf_selftest_umma(const float* A, const float* B, float* D, int N, int K, in
     if (!A || !B || !D || N < 16 || N > 256 || N % 16 || K < 32 || K % 32) return fail(MVF_ERR_INVALID, "mvf_selftest_umma: bad argument");
     MVF_RUN("mvf_selftest_umma", mvf::tc::umma_selftest(A, B, D, N, K, a_mn_major, (cudaStream_t)stream));
 }
+int mvf_selftest_umma_rows(const float* A, const float* B, float* D, int N, int K, int row_off, int base_off_mode, void* stream) {
+    if (!A || !B || !D || N < 16 || N > 256 || N % 16 || K < 32 || K % 32 || row_off < 0 || row_off > 32)
+        return fail(MVF_ERR_INVALID, "mvf_selftest_umma_rows: bad argument");
+    MVF_RUN("mvf_selftest_umma_rows", mvf::tc::umma_selftest(A, B, D, N, K, 0, (cudaStream_t)stream, row_off, base_off_mode));
+}
 void mvf_conv2d_debug_buffer(float* p) { mvf::tc::set_debug_buffer(p); }
 int mvf_conv2d_supported(const mvf_conv2d_desc* d) {
     if (!d) return 0;

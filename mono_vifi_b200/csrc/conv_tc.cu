@@ -188,6 +188,173 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
     }
 }
 
+
+// ---- stride-1 multi-tap convolutions: one haloed input patch per 32-channel block serves all taps -----------------
+// The per-tap kernel above pulls a fresh 16 KB A tile through L2 for every tap; here the producer loads, once per
+// 32-channel block, the patch of R input rows x P input columns that all KH*KW taps of the CTA's outputs read
+// (R = rows + KH - 1, P = columns + KW - 1).  The CTA's M rows are 128 CONSECUTIVE positions of that patch taken in
+// row-major order with pitch P ("flat-pitch" tile): output position m = r*P + j reads, for tap (kh,kw), patch row
+// m + kh*P + kw -- a uniform shift, so a tap is the same K-major operand with its start address moved by whole
+// 128-byte rows (the tensor core evaluates the 128B swizzle on absolute shared-memory address bits, so a start that
+// is not 1024-byte aligned is fine: mvf_selftest_umma_rows).  Positions with j > P - KW are padding columns whose
+// accumulator rows are never stored.  MT such 128-position tiles (stacked vertically, sharing one patch and every
+// filter tile) are accumulated side by side in TMEM to halve the filter traffic per MAC.
+struct PatchArgs {
+    float* y;
+    const float* bias;
+    long long y_sB, y_sH, y_sW;
+    int Cout, Ho, Wo;
+    int KH, KW, pad;
+    int P, PWo, TR, R;           // patch pitch, valid output columns per row, output rows per 128-position tile, patch rows
+    int nseg, tiles_y;           // column segments per image row, CTA rows per image
+    int n_cblk, act;
+    int patch_bytes, patch_stride;  // bytes landed per patch, distance between the two patch buffers (1024-aligned)
+};
+
+template <int N_TILE, int MT, int NB>
+__global__ void __launch_bounds__(NTHREADS) conv_patch_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                              const __grid_constant__ CUtensorMap mapB, const PatchArgs p) {
+    constexpr int B_STAGE_BYTES = N_TILE * BLOCK_K * 4;
+    constexpr int TMEM_COLS = (MT * N_TILE) < 32 ? 32 : (MT * N_TILE);
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smB = smem;
+    unsigned char* smA = smem + NB * B_STAGE_BYTES;  // NB * B_STAGE_BYTES is a multiple of 1024 for N_TILE >= 16 and NB = 4; see launch
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smA + 2 * p.patch_stride);
+    uint64_t* a_empty = a_full + 2;
+    uint64_t* b_full = a_empty + 2;
+    uint64_t* b_empty = b_full + NB;
+    uint64_t* tmem_full_bar = b_empty + NB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x;
+    const int seg = m % p.nseg, ty = (m / p.nseg) % p.tiles_y, b = m / (p.nseg * p.tiles_y);
+    const int xs = seg * p.PWo, ys = ty * (MT * p.TR), n0 = blockIdx.y * N_TILE;
+    const int taps = p.KH * p.KW;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < NB; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int bit = 0;
+            for (int cb = 0; cb < p.n_cblk; ++cb) {
+                const int ab = cb & 1;
+                mbar_wait(&a_empty[ab], ((cb >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&a_full[ab], p.patch_bytes);
+                // patch: dims (c, x, y, b), box (32, P, R, 1) at the CTA's input origin -> smem [R*P pixels][32 c]
+                tma_load_4d(smA + ab * p.patch_stride, &mapA, &a_full[ab], cb * BLOCK_K, xs - p.pad, ys - p.pad, b);
+                for (int t = 0; t < taps; ++t, ++bit) {
+                    const int s = bit % NB;
+                    mbar_wait(&b_empty[s], ((bit / NB) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&b_full[s], B_STAGE_BYTES);
+                    tma_load_3d(smB + s * B_STAGE_BYTES, &mapB, &b_full[s], 0, n0, t * p.n_cblk + cb);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(TILE_M, N_TILE, 0, 0);
+            int bit = 0;
+            for (int cb = 0; cb < p.n_cblk; ++cb) {
+                const int ab = cb & 1;
+                mbar_wait(&a_full[ab], (cb >> 1) & 1);
+                const uint32_t a_base = smem_u32(smA + ab * p.patch_stride);
+                for (int t = 0; t < taps; ++t, ++bit) {
+                    const int s = bit % NB;
+                    mbar_wait(&b_full[s], (bit / NB) & 1);
+                    tc_fence_after();
+                    const int kh = t / p.KW, kw = t - kh * p.KW;
+                    const uint32_t b_base = smem_u32(smB + s * B_STAGE_BYTES);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint32_t a_tap = a_base + (uint32_t)((mt * p.TR + kh) * p.P + kw) * 128u;
+#pragma unroll
+                        for (int kg = 0; kg < KGROUPS; ++kg) {
+                            const uint64_t adesc = make_smem_desc(a_tap + kg * 32, 16, 1024, SWZ_128B);
+                            const uint64_t bdesc = make_smem_desc(b_base + kg * 32, 16, 1024, SWZ_128B);
+                            umma_tf32(tmem_d + (uint32_t)(mt * N_TILE), adesc, bdesc, idesc, (cb > 0 || t > 0 || kg > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&b_empty[s]);
+                }
+                umma_commit(&a_empty[ab]);
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int mrow = q * 32 + lane;
+        const int r = mrow / p.P, j = mrow - r * p.P;
+        constexpr int CH = (N_TILE >= 32) ? 32 : 16;
+#pragma unroll 1
+        for (int mt = 0; mt < MT; ++mt) {
+            const int oy = ys + mt * p.TR + r, ox = xs + j;
+            const bool pix_ok = (r < p.TR) && (j < p.PWo) && (oy < p.Ho) && (ox < p.Wo);
+            float* ypix = p.y + (long long)b * p.y_sB + (long long)oy * p.y_sH + (long long)ox * p.y_sW;
+            const bool vec_ok = ((p.Cout & 3) == 0) && ((reinterpret_cast<uintptr_t>(ypix) & 15) == 0);
+#pragma unroll 1
+            for (int c0 = 0; c0 < N_TILE; c0 += CH) {
+                uint32_t rr[CH];
+                const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N_TILE + c0);
+                if constexpr (CH == 32) tmem_ld32(taddr, rr);
+                else tmem_ld16(taddr, rr);
+                tmem_ld_wait();
+                if (!pix_ok) continue;
+                float v[CH];
+#pragma unroll
+                for (int jj = 0; jj < CH; ++jj) {
+                    const int n = n0 + c0 + jj;
+                    float tval = __uint_as_float(rr[jj]);
+                    if (p.bias && n < p.Cout) tval += __ldg(p.bias + n);
+                    if (p.act == 1) tval = fmaxf(tval, 0.f);
+                    else if (p.act == 2) tval = tval > 0.f ? tval : expm1f(tval);
+                    v[jj] = tval;
+                }
+                if (vec_ok) {
+#pragma unroll
+                    for (int jj = 0; jj < CH; jj += 4)
+                        if (n0 + c0 + jj < p.Cout)
+                            *reinterpret_cast<float4*>(ypix + n0 + c0 + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < CH; ++jj)
+                        if (n0 + c0 + jj < p.Cout) ypix[n0 + c0 + jj] = v[jj];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_d, TMEM_COLS);
+    }
+}
+
 // ---- filter-bank packing -------------------------------------------------------------------------------------
 // fprop: Wp[tap][cb][co][kk] = w[co][cb*32+kk][kh][kw]                      (N = Cout, K = Cin)
 // dgrad: Wp[tap][cb][ci][kk] = w[cb*32+kk][ci][KH-1-kh][KW-1-kw]            (N = Cin,  K = Cout)
@@ -250,6 +417,21 @@ cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const ConvA
     return cudaGetLastError();
 }
 
+template <int N_TILE, int MT>
+cudaError_t launch_patch(const CUtensorMap& mapA, const CUtensorMap& mapB, const PatchArgs& a, int B, cudaStream_t st) {
+    constexpr int NB = 4;
+    const int smem = NB * N_TILE * BLOCK_K * 4 + 2 * a.patch_stride + 1024 + 256;
+    static int attr_max = 0;
+    if (smem > attr_max) {
+        cudaError_t e = cudaFuncSetAttribute(conv_patch_kernel<N_TILE, MT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_max = smem;
+    }
+    dim3 grid(B * a.nseg * a.tiles_y, (a.Cout + N_TILE - 1) / N_TILE);
+    conv_patch_kernel<N_TILE, MT, NB><<<grid, NTHREADS, smem, st>>>(mapA, mapB, a);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 size_t packed_filter_floats(int N, int K, int KH, int KW) {
@@ -279,6 +461,94 @@ const char* conv_check(const ConvDesc& d) {
 static float* g_dbg = nullptr;
 void set_debug_buffer(float* p) { g_dbg = p; }
 
+static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const float* w_packed, const float* bias, float* y,
+                                      int act, cudaStream_t st, const char** why, EncodeTiledFn enc, int Ho, int Wo) {
+    int n_tile = 16;
+    while (n_tile < d.Cout && n_tile < 128) n_tile *= 2;
+    const int n_ntiles = (d.Cout + n_tile - 1) / n_tile;
+    // column segmentation: the split of an output row into nseg pieces that needs the fewest 128-position tiles
+    int best_nseg = 1;
+    long long best_tiles = -1;
+    for (int nseg = 1; nseg <= 16; ++nseg) {
+        const int pwo = (Wo + nseg - 1) / nseg, P = pwo + d.KW - 1;
+        if (P > TILE_M) continue;
+        const int TR = TILE_M / P;
+        const long long tiles = (long long)nseg * ((Ho + TR - 1) / TR);
+        if (best_tiles < 0 || tiles < best_tiles) {
+            best_tiles = tiles;
+            best_nseg = nseg;
+        }
+    }
+    if (best_tiles < 0) {
+        *why = "output row too wide for the patch kernel";
+        return cudaErrorInvalidValue;
+    }
+    PatchArgs a;
+    a.y = y; a.bias = bias;
+    a.y_sB = d.y_sB; a.y_sH = d.y_sH; a.y_sW = d.y_sW;
+    a.Cout = d.Cout; a.Ho = Ho; a.Wo = Wo; a.KH = d.KH; a.KW = d.KW; a.pad = d.pad;
+    a.nseg = best_nseg;
+    a.PWo = (Wo + best_nseg - 1) / best_nseg;
+    a.P = a.PWo + d.KW - 1;
+    a.TR = TILE_M / a.P;
+    // two stacked tiles per CTA (shared patch and filter tiles) when that still leaves about two waves of CTAs
+    int MT = 1;
+    {
+        const long long ctas2 = (long long)d.B * best_nseg * ((Ho + 2 * a.TR - 1) / (2 * a.TR)) * n_ntiles;
+        if (ctas2 >= 2 * 148 && Ho >= 2 * a.TR) MT = 2;
+    }
+    a.R = MT * a.TR + d.KH - 1;
+    a.tiles_y = (Ho + MT * a.TR - 1) / (MT * a.TR);
+    a.n_cblk = (d.Cin + BLOCK_K - 1) / BLOCK_K;
+    a.act = act;
+    a.patch_bytes = a.R * a.P * BLOCK_K * 4;
+    // the MMAs of the last taps read up to (KW - 1) rows past R*P for positions that are never stored; keep them inside the buffer
+    a.patch_stride = ((a.patch_bytes + (d.KW - 1 + TILE_M - a.TR * a.P) * 128) + 1023) / 1024 * 1024;
+    if (4 * n_tile * BLOCK_K * 4 + 2 * a.patch_stride + 1280 > 227 * 1024) {
+        *why = "patch does not fit in shared memory";
+        return cudaErrorInvalidValue;
+    }
+    CUtensorMap mapA, mapB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)d.x_sW * 4, (cuuint64_t)d.x_sH * 4, (cuuint64_t)d.x_sB * 4};
+        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)a.P, (cuuint32_t)a.R, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        if (enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            *why = "cuTensorMapEncodeTiled failed for the input patch";
+            return cudaErrorInvalidValue;
+        }
+    }
+    {
+        cuuint64_t dims[3] = {BLOCK_K, (cuuint64_t)d.Cout, (cuuint64_t)(d.KH * d.KW * a.n_cblk)};
+        cuuint64_t strides[2] = {BLOCK_K * 4, (cuuint64_t)d.Cout * BLOCK_K * 4};
+        cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)n_tile, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        if (enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w_packed), dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            *why = "cuTensorMapEncodeTiled failed for the packed filter bank";
+            return cudaErrorInvalidValue;
+        }
+    }
+    if (MT == 2) {
+        switch (n_tile) {
+            case 16: return launch_patch<16, 2>(mapA, mapB, a, d.B, st);
+            case 32: return launch_patch<32, 2>(mapA, mapB, a, d.B, st);
+            case 64: return launch_patch<64, 2>(mapA, mapB, a, d.B, st);
+            default: return launch_patch<128, 2>(mapA, mapB, a, d.B, st);
+        }
+    }
+    switch (n_tile) {
+        case 16: return launch_patch<16, 1>(mapA, mapB, a, d.B, st);
+        case 32: return launch_patch<32, 1>(mapA, mapB, a, d.B, st);
+        case 64: return launch_patch<64, 1>(mapA, mapB, a, d.B, st);
+        default: return launch_patch<128, 1>(mapA, mapB, a, d.B, st);
+    }
+}
+
 cudaError_t conv_forward(const ConvDesc& d, const float* x, const float* w_packed, const float* bias, float* y, int act,
                          cudaStream_t st, const char** why) {
     *why = nullptr;
@@ -292,6 +562,8 @@ cudaError_t conv_forward(const ConvDesc& d, const float* x, const float* w_packe
         return cudaErrorInvalidValue;
     }
     const int Ho = out_size(d.H, d.KH, d.pad, d.stride), Wo = out_size(d.W, d.KW, d.pad, d.stride);
+    if (d.stride == 1 && d.KH * d.KW > 1 && d.KW <= 16 && !getenv("MVF_CONV_NO_PATCH"))
+        return conv_forward_patch(d, x, w_packed, bias, y, act, st, why, enc, Ho, Wo);
     ConvArgs a;
     a.y = y;
     a.bias = bias;

@@ -29,7 +29,8 @@ cudaError_t conv_wgrad(const WgradDesc& d, const float* x, const float* gy, floa
 
 size_t packed_filter_floats(int N, int K, int KH, int KW);
 cudaError_t pack_filters(const float* w, float* out, int Cout, int Cin, int KH, int KW, int dgrad, cudaStream_t st);
-cudaError_t umma_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn_major, cudaStream_t st);
+cudaError_t umma_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn_major, cudaStream_t st,
+                          int row_off = 0, int base_off_mode = 0);
 void set_debug_buffer(float* p);  // development aid: dump of pipeline stage 0, see conv_tc.cu
 const char* conv_check(const ConvDesc& d);  // nullptr if the tcgen05 path covers the problem, else the reason
 cudaError_t conv_forward(const ConvDesc& d, const float* x, const float* w_packed, const float* bias, float* y, int act,

@@ -11,12 +11,12 @@ namespace {
 
 __global__ void __launch_bounds__(128) umma_selftest_kernel(const __grid_constant__ CUtensorMap mapA,
                                                             const __grid_constant__ CUtensorMap mapB, float* D, int N, int K,
-                                                            int a_mn_major) {
+                                                            int a_mn_major, int row_off, int base_off_mode) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* smA = smem;           // 16 KB: 128 x 32 floats
-    unsigned char* smB = smem + 16384;   // up to 32 KB: N x 32 floats
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 16384 + 32768);
+    unsigned char* smA = smem;           // 20 KB: 160 x 32 floats (K-major) / 16 KB + slack (MN-major)
+    unsigned char* smB = smem + 20480;   // up to 32 KB: N x 32 floats
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 20480 + 32768);
     uint64_t* mma_bar = full_bar + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -37,12 +37,12 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __grid_constan
     const int nkb = K / 32;
     for (int kb = 0; kb < nkb; ++kb) {
         if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(full_bar, 16384 + N * 128);
+            mbar_arrive_expect_tx(full_bar, (a_mn_major ? 16384 : 20480) + N * 128);
             if (a_mn_major) {
                 // A given as [K][128]: dims (m%32, k%8, m/32, k/8), box (32, 8, 4, 4) -> smem [k/8][m/32][k%8][m%32]
                 tma_load_4d(smA, &mapA, full_bar, 0, 0, 0, kb * 4);
             } else {
-                tma_load_3d(smA, &mapA, full_bar, 0, 0, kb);  // dims (k%32, m, k/32), box (32, 128, 1)
+                tma_load_3d(smA, &mapA, full_bar, 0, 0, kb);  // dims (k%32, m, k/32), box (32, 160, 1)
             }
             tma_load_3d(smB, &mapB, full_bar, 0, 0, kb);
             mbar_wait(full_bar, kb & 1);
@@ -50,7 +50,12 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __grid_constan
             for (int kg = 0; kg < 4; ++kg) {
                 uint64_t adesc, bdesc;
                 if (a_mn_major) adesc = make_smem_desc(smem_u32(smA) + kg * 4096, 1024, 512, SWZ_128B_BASE32B);
-                else adesc = make_smem_desc(smem_u32(smA) + kg * 32, 16, 1024, SWZ_128B);
+                else {
+                    // experiment: operand = rows [row_off, row_off + 128) of the 160 loaded rows (start not 1024-aligned)
+                    const uint32_t start = smem_u32(smA) + row_off * 128 + kg * 32;
+                    adesc = make_smem_desc(start, 16, 1024, SWZ_128B);
+                    if (base_off_mode == 1) adesc |= (uint64_t)((start >> 7) & 7) << 49;
+                }
                 bdesc = make_smem_desc(smem_u32(smB) + kg * 32, 16, 1024, SWZ_128B);
                 umma_tf32(tmem_d, adesc, bdesc, idesc, (kb > 0 || kg > 0) ? 1u : 0u);
             }
@@ -76,8 +81,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 }  // namespace
 
-// A: [128][K] (a_mn_major = 0) or [K][128] (a_mn_major = 1); B: [N][K]; D: [128][N].  K % 32 == 0, N % 16 == 0, N <= 256.
-cudaError_t umma_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn_major, cudaStream_t st) {
+// A: [160][K] of which rows [row_off, row_off+128) are used (a_mn_major = 0) or [K][128] (a_mn_major = 1); B: [N][K];
+// D: [128][N].  K % 32 == 0, N % 16 == 0, N <= 256.
+cudaError_t umma_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn_major, cudaStream_t st,
+                          int row_off, int base_off_mode) {
     void* fp = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) != cudaSuccess || !fp)
@@ -94,9 +101,9 @@ cudaError_t umma_selftest(const float* A, const float* B, float* D, int N, int K
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
     } else {
-        cuuint64_t dims[3] = {32, 128, (cuuint64_t)(K / 32)};
+        cuuint64_t dims[3] = {32, 160, (cuuint64_t)(K / 32)};  // A holds 160 rows; the product uses 128 of them
         cuuint64_t strides[2] = {(cuuint64_t)K * 4, 128};
-        cuuint32_t box[3] = {32, 128, 1};
+        cuuint32_t box[3] = {32, 160, 1};
         if (enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(A), dims, strides, box, es,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -111,10 +118,10 @@ cudaError_t umma_selftest(const float* A, const float* B, float* D, int N, int K
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
     }
-    const int smem = 16384 + 32768 + 1024 + 64;
+    const int smem = 20480 + 32768 + 1024 + 64;
     cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    umma_selftest_kernel<<<1, 128, smem, st>>>(mapA, mapB, D, N, K, a_mn_major);
+    umma_selftest_kernel<<<1, 128, smem, st>>>(mapA, mapB, D, N, K, a_mn_major, row_off, base_off_mode);
     return cudaGetLastError();
 }
 

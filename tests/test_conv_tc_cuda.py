@@ -30,6 +30,12 @@ CASES = [
     (2, 64, 24, 80, 128, 1, 0, 2, False),   # 1x1 stride 2 (downsample)
     (1, 8, 33, 71, 64, 7, 3, 2, False),     # 7x7 stride 2 stem on odd sizes (image channels padded 3 -> 8)
     (1, 4, 16, 32, 16, 3, 1, 1, False),     # four input channels (16-byte pixels)
+    (12, 64, 48, 160, 64, 3, 1, 1, True),   # ResNet layer1 at the benchmark size: 4 column segments, 2 stacked tiles per CTA
+    (2, 16, 64, 640, 16, 3, 1, 1, False),   # full-resolution decoder layer: 6 column segments of 107
+    (2, 32, 32, 322, 16, 3, 0, 1, True),    # reflection-padded input of a 320-wide layer (valid conv)
+    (3, 128, 24, 80, 128, 3, 1, 1, False),  # 2 segments x 3 rows
+    (2, 64, 7, 9, 32, 5, 2, 1, False),      # 5x5 filter, tiny image
+    (1, 32, 5, 300, 16, 1, 0, 1, False),    # 1x1 on a wide image (per-tap kernel)
 ]
 
 
