@@ -154,6 +154,15 @@ size_t mvf_conv2d_wgrad_workspace_floats(const mvf_conv2d_desc* d);
 int mvf_conv2d_wgrad(const mvf_conv2d_desc* d, const float* x, const float* grad_out, float* grad_w, float* workspace,
                      size_t workspace_floats, void* stream);
 
+/* ---- fused nearest-upsample x2 + channel concat + ReflectionPad2d(1), channels-last ---------------------------------
+ * y[B,Ca+Cs,H+2,W+2] = pad(cat(upsample ? up2(a[B,Ca,H/2,W/2]) : a[B,Ca,H,W], skip[B,Cs,H,W])): the data movement
+ * the reference does with F.interpolate + torch.cat + nn.ReflectionPad2d(1) before each decoder convolution
+ * (monodepth2.py:86-93, layers.py:126-139), in one pass; bwd is the exact adjoint.  Dense channels-last buffers
+ * (element (b,c,y,x) at ((b*H + y)*W + x)*C + c), channel counts % 4 == 0, H, W >= 4.  skip may be NULL (Cs = 0). */
+int mvf_upcat_pad_fwd(const float* a, const float* skip, float* y, int B, int Ca, int Cs, int H, int W, int upsample, void* stream);
+int mvf_upcat_pad_bwd(const float* grad_y, float* grad_a, float* grad_skip, int B, int Ca, int Cs, int H, int W, int upsample,
+                      void* stream);
+
 /* device self-test: q_sequence[i] = the kernels' shared-reciprocal division of a[i] by b[i], q_ieee[i] = the
  * IEEE quotient (div.rn.f32); the two must be bit-identical for operands in the normal range. */
 int mvf_selftest_division(const float* a, const float* b, float* q_sequence, float* q_ieee, size_t n, void* stream);

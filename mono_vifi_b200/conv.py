@@ -32,7 +32,15 @@ def get_backend():
     return _backend
 
 
-def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+def _activate(y, act):
+    if act == "relu":
+        return F.relu(y)
+    if act == "elu":
+        return F.elu(y)
+    return y
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, act=None):
     if _backend == "tcgen05" and x.is_cuda:
         from . import conv_tc
         cin = weight.shape[1]
@@ -43,9 +51,9 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
             weight = F.pad(weight, (0, 0, 0, 0, 0, extra))
         if conv_tc.supported(x, weight, stride, padding, dilation, groups):
             stats["tcgen05"] += 1
-            return conv_tc.conv2d(x, weight, bias, stride, padding)
+            return conv_tc.conv2d(x, weight, bias, stride, padding, act=act)
     stats["cudnn"] += 1
-    return F.conv2d(x, weight, bias, stride, padding, dilation, groups)
+    return _activate(F.conv2d(x, weight, bias, stride, padding, dilation, groups), act)
 
 
 class Conv2d(nn.Conv2d):

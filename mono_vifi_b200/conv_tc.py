@@ -105,23 +105,33 @@ def conv_forward_raw(x, w_packed, bias, Cout, KH, KW, pad, stride=1, act=0, out=
     return y
 
 
+ACT = {None: 0, "none": 0, "relu": 1, "elu": 2}
+
+
 class _Conv2dTC(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, pad, stride):
+    def forward(ctx, x, weight, bias, pad, stride, act):
         Cout, Cin, KH, KW = weight.shape
         launches["fprop"] += 1
         x = _as_input(x)
-        y = conv_forward_raw(x, pack_filters(weight), bias, Cout, KH, KW, pad, stride)
-        ctx.save_for_backward(x, weight)
-        ctx.pad, ctx.stride, ctx.has_bias = pad, stride, bias is not None
+        y = conv_forward_raw(x, pack_filters(weight), bias, Cout, KH, KW, pad, stride, act=act)  # activation in the epilogue
+        if act:
+            ctx.save_for_backward(x, weight, y)
+        else:
+            ctx.save_for_backward(x, weight)
+        ctx.pad, ctx.stride, ctx.has_bias, ctx.act = pad, stride, bias is not None, act
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, weight = ctx.saved_tensors
+        x, weight = ctx.saved_tensors[:2]
         Cout, Cin, KH, KW = weight.shape
         pad, stride = ctx.pad, ctx.stride
         gx = gw = gb = None
+        if ctx.act == 1:
+            gy = torch.ops.aten.threshold_backward(gy, ctx.saved_tensors[2], 0.0)
+        elif ctx.act == 2:  # d elu / d pre-activation from the saved OUTPUT: 1 where y > 0, y + 1 elsewhere
+            gy = torch.ops.aten.elu_backward(gy, 1.0, 1.0, 1.0, True, ctx.saved_tensors[2])
         gy = _as_input(gy)
         if ctx.needs_input_grad[0]:
             if stride == 1 and Cout % 4 == 0 and pad <= KH - 1 and pad <= KW - 1:
@@ -138,7 +148,7 @@ class _Conv2dTC(torch.autograd.Function):
             gw = weight_grad(x, gy, weight.shape, pad, stride)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gy.sum((0, 2, 3))
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
 def input_grad_library(x, gy, weight, pad, stride):
@@ -185,7 +195,8 @@ def weight_grad(x, gy, wshape, pad, stride=1):
     return gw
 
 
-def conv2d(x, weight, bias=None, stride=1, padding=0):
+def conv2d(x, weight, bias=None, stride=1, padding=0, act=None):
+    """act: None | "relu" | "elu" -- applied in the kernel's epilogue (its backward uses the saved output)."""
     pad = padding if isinstance(padding, int) else padding[0]
     st = stride if isinstance(stride, int) else stride[0]
-    return _Conv2dTC.apply(x, weight, bias, pad, st)
+    return _Conv2dTC.apply(x, weight, bias, pad, st, ACT[act])

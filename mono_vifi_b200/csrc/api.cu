@@ -7,6 +7,7 @@
 #include "conv_tc.cuh"
 #include "f1.cuh"
 #include "ops.cuh"
+#include "ops_cl.cuh"
 
 namespace {
 thread_local char g_err[512] = "";
@@ -285,6 +286,20 @@ int mvf_conv2d_wgrad(const mvf_conv2d_desc* d, const float* x, const float* grad
     cudaError_t e = mvf::tc::conv_wgrad(c, x, grad_out, grad_w, workspace, (cudaStream_t)stream, &why);
     if (e != cudaSuccess) return why ? fail(MVF_ERR_CUDA, why) : fail(MVF_ERR_CUDA, "mvf_conv2d_wgrad launch", e);
     return MVF_OK;
+}
+
+/* ---- fused upsample + concat + reflection pad (channels-last) --------------------------------------------------- */
+int mvf_upcat_pad_fwd(const float* a, const float* skip, float* y, int B, int Ca, int Cs, int H, int W, int upsample, void* stream) {
+    if (!a || !y || B <= 0 || Ca <= 0 || Cs < 0 || (Cs > 0 && !skip) || H < 4 || W < 4 || (Ca % 4) || (Cs % 4) ||
+        (upsample && ((H | W) & 1)))
+        return fail(MVF_ERR_INVALID, "mvf_upcat_pad_fwd: need channels % 4 == 0, H, W >= 4 (even when upsampling)");
+    MVF_RUN("mvf_upcat_pad_fwd", mvf::upcat_pad_fwd(a, skip, y, B, Ca, Cs, H, W, upsample, (cudaStream_t)stream));
+}
+int mvf_upcat_pad_bwd(const float* grad_y, float* grad_a, float* grad_skip, int B, int Ca, int Cs, int H, int W, int upsample,
+                      void* stream) {
+    if (!grad_y || B <= 0 || Ca <= 0 || Cs < 0 || H < 4 || W < 4 || (Ca % 4) || (Cs % 4) || (upsample && ((H | W) & 1)))
+        return fail(MVF_ERR_INVALID, "mvf_upcat_pad_bwd: need channels % 4 == 0, H, W >= 4 (even when upsampling)");
+    MVF_RUN("mvf_upcat_pad_bwd", mvf::upcat_pad_bwd(grad_y, grad_a, grad_skip, B, Ca, Cs, H, W, upsample, (cudaStream_t)stream));
 }
 
 }  // extern "C"

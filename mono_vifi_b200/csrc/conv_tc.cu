@@ -209,28 +209,32 @@ struct PatchArgs {
     int nseg, tiles_y;           // column segments per image row, CTA rows per image
     int n_cblk, act;
     int patch_bytes, patch_stride;  // bytes landed per patch, distance between the two patch buffers (1024-aligned)
+    int n_mtiles, n_tiles;       // M tiles (B * nseg * tiles_y), all tiles (M tiles x N tiles)
+    int dbg;                     // timing experiments only: 4 = no MMAs, 8 = no TMA loads, 16 = no stores, 32 = no epilogue
 };
 
+// Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA producer runs ahead across
+// tile boundaries (patch double buffer + NB-deep filter ring), the MMA issuer alternates between two accumulator
+// buffers in TMEM, and the four epilogue warps drain one buffer while the next tile is being multiplied.
 template <int N_TILE, int MT, int NB>
-__global__ void __launch_bounds__(NTHREADS) conv_patch_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                              const __grid_constant__ CUtensorMap mapB, const PatchArgs p) {
+__global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                 const __grid_constant__ CUtensorMap mapB, const PatchArgs p) {
     constexpr int B_STAGE_BYTES = N_TILE * BLOCK_K * 4;
-    constexpr int TMEM_COLS = (MT * N_TILE) < 32 ? 32 : (MT * N_TILE);
+    constexpr int ACC_COLS = MT * N_TILE;  // one accumulator buffer
+    constexpr int TMEM_COLS = (2 * ACC_COLS) < 32 ? 32 : (2 * ACC_COLS);
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* smB = smem;
-    unsigned char* smA = smem + NB * B_STAGE_BYTES;  // NB * B_STAGE_BYTES is a multiple of 1024 for N_TILE >= 16 and NB = 4; see launch
+    unsigned char* smA = smem + NB * B_STAGE_BYTES;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smA + 2 * p.patch_stride);
     uint64_t* a_empty = a_full + 2;
     uint64_t* b_full = a_empty + 2;
     uint64_t* b_empty = b_full + NB;
-    uint64_t* tmem_full_bar = b_empty + NB;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* acc_full = b_empty + NB;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m = blockIdx.x;
-    const int seg = m % p.nseg, ty = (m / p.nseg) % p.tiles_y, b = m / (p.nseg * p.tiles_y);
-    const int xs = seg * p.PWo, ys = ty * (MT * p.TR), n0 = blockIdx.y * N_TILE;
     const int taps = p.KH * p.KW;
 
     if (warp == 0 && lane == 0) {
@@ -239,12 +243,13 @@ __global__ void __launch_bounds__(NTHREADS) conv_patch_kernel(const __grid_const
         for (int s = 0; s < 2; ++s) {
             mbar_init(&a_full[s], 1);
             mbar_init(&a_empty[s], 1);
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 128);  // every epilogue thread arrives
         }
         for (int s = 0; s < NB; ++s) {
             mbar_init(&b_full[s], 1);
             mbar_init(&b_empty[s], 1);
         }
-        mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -257,94 +262,133 @@ __global__ void __launch_bounds__(NTHREADS) conv_patch_kernel(const __grid_const
     const uint32_t tmem_d = *tmem_slot;
 
     if (warp == 0) {
+        // ===== TMA producer (one lane) =====
         if (lane == 0) {
-            int bit = 0;
-            for (int cb = 0; cb < p.n_cblk; ++cb) {
-                const int ab = cb & 1;
-                mbar_wait(&a_empty[ab], ((cb >> 1) & 1) ^ 1);
-                mbar_arrive_expect_tx(&a_full[ab], p.patch_bytes);
-                // patch: dims (c, x, y, b), box (32, P, R, 1) at the CTA's input origin -> smem [R*P pixels][32 c]
-                tma_load_4d(smA + ab * p.patch_stride, &mapA, &a_full[ab], cb * BLOCK_K, xs - p.pad, ys - p.pad, b);
-                for (int t = 0; t < taps; ++t, ++bit) {
-                    const int s = bit % NB;
-                    mbar_wait(&b_empty[s], ((bit / NB) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&b_full[s], B_STAGE_BYTES);
-                    tma_load_3d(smB + s * B_STAGE_BYTES, &mapB, &b_full[s], 0, n0, t * p.n_cblk + cb);
+            int bs = 0, bph = 0;  // filter ring slot / phase
+            int ab = 0, aph = 0;  // patch buffer / phase
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+                const int m = t % p.n_mtiles, nt = t / p.n_mtiles;
+                const int seg = m % p.nseg, ty = (m / p.nseg) % p.tiles_y, b = m / (p.nseg * p.tiles_y);
+                const int xs = seg * p.PWo, ys = ty * (MT * p.TR), n0 = nt * N_TILE;
+                for (int cb = 0; cb < p.n_cblk; ++cb) {
+                    mbar_wait(&a_empty[ab], aph ^ 1);
+                    if (p.dbg & 8) {
+                        mbar_arrive(&a_full[ab]);
+                    } else {
+                        mbar_arrive_expect_tx(&a_full[ab], p.patch_bytes);
+                        // patch: dims (c, x, y, b), box (32, P, R, 1) at the tile's input origin -> smem [R*P pixels][32 c]
+                        tma_load_4d(smA + ab * p.patch_stride, &mapA, &a_full[ab], cb * BLOCK_K, xs - p.pad, ys - p.pad, b);
+                    }
+                    if (++ab == 2) { ab = 0; aph ^= 1; }
+                    int kb = cb;  // filter tile index = tap * n_cblk + cb
+                    for (int tp = 0; tp < taps; ++tp, kb += p.n_cblk) {
+                        mbar_wait(&b_empty[bs], bph ^ 1);
+                        if (p.dbg & 8) {
+                            mbar_arrive(&b_full[bs]);
+                        } else {
+                            mbar_arrive_expect_tx(&b_full[bs], B_STAGE_BYTES);
+                            tma_load_3d(smB + bs * B_STAGE_BYTES, &mapB, &b_full[bs], 0, n0, kb);
+                        }
+                        if (++bs == NB) { bs = 0; bph ^= 1; }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(TILE_M, N_TILE, 0, 0);
-            int bit = 0;
+        // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues =====
+        constexpr uint32_t idesc = make_idesc_tf32(TILE_M, N_TILE, 0, 0);
+        const uint64_t desc_hi = make_smem_desc(0, 16, 1024, SWZ_128B);  // everything but the start address
+        const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
+        int bs = 0, bph = 0, ab = 0, aph = 0, acc = 0, accph = 0;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+            mbar_wait(&acc_empty[acc], accph ^ 1);  // the epilogue has drained this accumulator buffer
+            tc_fence_after();
+            const uint32_t d_base = tmem_d + (uint32_t)(acc * ACC_COLS);
             for (int cb = 0; cb < p.n_cblk; ++cb) {
-                const int ab = cb & 1;
-                mbar_wait(&a_full[ab], (cb >> 1) & 1);
-                const uint32_t a_base = smem_u32(smA + ab * p.patch_stride);
-                for (int t = 0; t < taps; ++t, ++bit) {
-                    const int s = bit % NB;
-                    mbar_wait(&b_full[s], (bit / NB) & 1);
+                mbar_wait(&a_full[ab], aph);
+                const uint32_t a_base = smA_u + (uint32_t)(ab * p.patch_stride);
+                int kh = 0, kw = 0;
+                for (int tp = 0; tp < taps; ++tp) {
+                    mbar_wait(&b_full[bs], bph);
                     tc_fence_after();
-                    const int kh = t / p.KW, kw = t - kh * p.KW;
-                    const uint32_t b_base = smem_u32(smB + s * B_STAGE_BYTES);
+                    const uint32_t b_lo = (smB_u + (uint32_t)(bs * B_STAGE_BYTES)) >> 4;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const uint32_t a_tap = a_base + (uint32_t)((mt * p.TR + kh) * p.P + kw) * 128u;
+                        for (int mt = 0; mt < MT; ++mt) {
+                            if (p.dbg & 4) break;
+                            const uint32_t a_lo = (a_base + (uint32_t)((mt * p.TR + kh) * p.P + kw) * 128u) >> 4;
 #pragma unroll
-                        for (int kg = 0; kg < KGROUPS; ++kg) {
-                            const uint64_t adesc = make_smem_desc(a_tap + kg * 32, 16, 1024, SWZ_128B);
-                            const uint64_t bdesc = make_smem_desc(b_base + kg * 32, 16, 1024, SWZ_128B);
-                            umma_tf32(tmem_d + (uint32_t)(mt * N_TILE), adesc, bdesc, idesc, (cb > 0 || t > 0 || kg > 0) ? 1u : 0u);
+                            for (int kg = 0; kg < KGROUPS; ++kg)
+                                umma_tf32(d_base + (uint32_t)(mt * N_TILE), desc_hi | (uint64_t)(a_lo + 2 * kg),
+                                          desc_hi | (uint64_t)(b_lo + 2 * kg), idesc, (cb > 0 || tp > 0 || kg > 0) ? 1u : 0u);
                         }
+                        umma_commit(&b_empty[bs]);
                     }
-                    umma_commit(&b_empty[s]);
+                    __syncwarp();
+                    if (++bs == NB) { bs = 0; bph ^= 1; }
+                    if (++kw == p.KW) { kw = 0; ++kh; }
                 }
-                umma_commit(&a_empty[ab]);
+                if (elect_one()) umma_commit(&a_empty[ab]);
+                __syncwarp();
+                if (++ab == 2) { ab = 0; aph ^= 1; }
             }
-            umma_commit(tmem_full_bar);
+            if (elect_one()) umma_commit(&acc_full[acc]);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; accph ^= 1; }
         }
     } else {
+        // ===== epilogue: warps 2..5 own the TMEM lane quarter (warp % 4); one thread = one patch position =====
         const int q = warp & 3;
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
         const int mrow = q * 32 + lane;
         const int r = mrow / p.P, j = mrow - r * p.P;
         constexpr int CH = (N_TILE >= 32) ? 32 : 16;
+        int acc = 0, accph = 0;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+            const int m = t % p.n_mtiles, nt = t / p.n_mtiles;
+            const int seg = m % p.nseg, ty = (m / p.nseg) % p.tiles_y, b = m / (p.nseg * p.tiles_y);
+            const int xs = seg * p.PWo, ys = ty * (MT * p.TR), n0 = nt * N_TILE;
+            mbar_wait(&acc_full[acc], accph);
+            tc_fence_after();
 #pragma unroll 1
-        for (int mt = 0; mt < MT; ++mt) {
-            const int oy = ys + mt * p.TR + r, ox = xs + j;
-            const bool pix_ok = (r < p.TR) && (j < p.PWo) && (oy < p.Ho) && (ox < p.Wo);
-            float* ypix = p.y + (long long)b * p.y_sB + (long long)oy * p.y_sH + (long long)ox * p.y_sW;
-            const bool vec_ok = ((p.Cout & 3) == 0) && ((reinterpret_cast<uintptr_t>(ypix) & 15) == 0);
+            for (int mt = 0; mt < MT; ++mt) {
+                if (p.dbg & 32) break;
+                const int oy = ys + mt * p.TR + r, ox = xs + j;
+                const bool pix_ok = (r < p.TR) && (j < p.PWo) && (oy < p.Ho) && (ox < p.Wo) && !(p.dbg & 16);
+                float* ypix = p.y + (long long)b * p.y_sB + (long long)oy * p.y_sH + (long long)ox * p.y_sW;
+                const bool vec_ok = ((p.Cout & 3) == 0) && ((reinterpret_cast<uintptr_t>(ypix) & 15) == 0);
 #pragma unroll 1
-            for (int c0 = 0; c0 < N_TILE; c0 += CH) {
-                uint32_t rr[CH];
-                const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N_TILE + c0);
-                if constexpr (CH == 32) tmem_ld32(taddr, rr);
-                else tmem_ld16(taddr, rr);
-                tmem_ld_wait();
-                if (!pix_ok) continue;
-                float v[CH];
+                for (int c0 = 0; c0 < N_TILE; c0 += CH) {
+                    uint32_t rr[CH];
+                    const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + mt * N_TILE + c0);
+                    if constexpr (CH == 32) tmem_ld32(taddr, rr);
+                    else tmem_ld16(taddr, rr);
+                    tmem_ld_wait();
+                    if (!pix_ok) continue;
+                    float v[CH];
 #pragma unroll
-                for (int jj = 0; jj < CH; ++jj) {
-                    const int n = n0 + c0 + jj;
-                    float tval = __uint_as_float(rr[jj]);
-                    if (p.bias && n < p.Cout) tval += __ldg(p.bias + n);
-                    if (p.act == 1) tval = fmaxf(tval, 0.f);
-                    else if (p.act == 2) tval = tval > 0.f ? tval : expm1f(tval);
-                    v[jj] = tval;
-                }
-                if (vec_ok) {
+                    for (int jj = 0; jj < CH; ++jj) {
+                        const int n = n0 + c0 + jj;
+                        float tval = __uint_as_float(rr[jj]);
+                        if (p.bias && n < p.Cout) tval += __ldg(p.bias + n);
+                        if (p.act == 1) tval = fmaxf(tval, 0.f);
+                        else if (p.act == 2) tval = tval > 0.f ? tval : expm1f(tval);
+                        v[jj] = tval;
+                    }
+                    if (vec_ok) {
 #pragma unroll
-                    for (int jj = 0; jj < CH; jj += 4)
-                        if (n0 + c0 + jj < p.Cout)
-                            *reinterpret_cast<float4*>(ypix + n0 + c0 + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
-                } else {
+                        for (int jj = 0; jj < CH; jj += 4)
+                            if (n0 + c0 + jj < p.Cout)
+                                *reinterpret_cast<float4*>(ypix + n0 + c0 + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+                    } else {
 #pragma unroll
-                    for (int jj = 0; jj < CH; ++jj)
-                        if (n0 + c0 + jj < p.Cout) ypix[n0 + c0 + jj] = v[jj];
+                        for (int jj = 0; jj < CH; ++jj)
+                            if (n0 + c0 + jj < p.Cout) ypix[n0 + c0 + jj] = v[jj];
+                    }
                 }
             }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);  // this thread's TMEM reads of the buffer are complete
+            if (++acc == 2) { acc = 0; accph ^= 1; }
         }
     }
     tc_fence_before();
@@ -418,8 +462,8 @@ cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const ConvA
 }
 
 template <int N_TILE, int MT>
-cudaError_t launch_patch(const CUtensorMap& mapA, const CUtensorMap& mapB, const PatchArgs& a, int B, cudaStream_t st) {
-    constexpr int NB = 4;
+cudaError_t launch_patch(const CUtensorMap& mapA, const CUtensorMap& mapB, const PatchArgs& a, cudaStream_t st) {
+    constexpr int NB = (N_TILE >= 128) ? 6 : 8;  // 96 KB / 64 KB / 32 KB / 16 KB of filter tiles in flight
     const int smem = NB * N_TILE * BLOCK_K * 4 + 2 * a.patch_stride + 1024 + 256;
     static int attr_max = 0;
     if (smem > attr_max) {
@@ -427,7 +471,14 @@ cudaError_t launch_patch(const CUtensorMap& mapA, const CUtensorMap& mapB, const
         if (e != cudaSuccess) return e;
         attr_max = smem;
     }
-    dim3 grid(B * a.nseg * a.tiles_y, (a.Cout + N_TILE - 1) / N_TILE);
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    const int grid = a.n_tiles < n_sm ? a.n_tiles : n_sm;
     conv_patch_kernel<N_TILE, MT, NB><<<grid, NTHREADS, smem, st>>>(mapA, mapB, a);
     return cudaGetLastError();
 }
@@ -495,7 +546,7 @@ static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const f
     int MT = 1;
     {
         const long long ctas2 = (long long)d.B * best_nseg * ((Ho + 2 * a.TR - 1) / (2 * a.TR)) * n_ntiles;
-        if (ctas2 >= 2 * 148 && Ho >= 2 * a.TR) MT = 2;
+        if (ctas2 >= 2 * 148 && Ho >= 2 * a.TR && !getenv("MVF_CONV_MT1")) MT = 2;
     }
     a.R = MT * a.TR + d.KH - 1;
     a.tiles_y = (Ho + MT * a.TR - 1) / (MT * a.TR);
@@ -504,7 +555,10 @@ static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const f
     a.patch_bytes = a.R * a.P * BLOCK_K * 4;
     // the MMAs of the last taps read up to (KW - 1) rows past R*P for positions that are never stored; keep them inside the buffer
     a.patch_stride = ((a.patch_bytes + (d.KW - 1 + TILE_M - a.TR * a.P) * 128) + 1023) / 1024 * 1024;
-    if (4 * n_tile * BLOCK_K * 4 + 2 * a.patch_stride + 1280 > 227 * 1024) {
+    a.dbg = getenv("MVF_CONV_DBG") ? atoi(getenv("MVF_CONV_DBG")) : 0;
+    a.n_mtiles = d.B * a.nseg * a.tiles_y;
+    a.n_tiles = a.n_mtiles * n_ntiles;
+    if ((n_tile >= 128 ? 6 : 8) * n_tile * BLOCK_K * 4 + 2 * a.patch_stride + 1280 > 227 * 1024) {
         *why = "patch does not fit in shared memory";
         return cudaErrorInvalidValue;
     }
@@ -535,17 +589,17 @@ static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const f
     }
     if (MT == 2) {
         switch (n_tile) {
-            case 16: return launch_patch<16, 2>(mapA, mapB, a, d.B, st);
-            case 32: return launch_patch<32, 2>(mapA, mapB, a, d.B, st);
-            case 64: return launch_patch<64, 2>(mapA, mapB, a, d.B, st);
-            default: return launch_patch<128, 2>(mapA, mapB, a, d.B, st);
+            case 16: return launch_patch<16, 2>(mapA, mapB, a, st);
+            case 32: return launch_patch<32, 2>(mapA, mapB, a, st);
+            case 64: return launch_patch<64, 2>(mapA, mapB, a, st);
+            default: return launch_patch<128, 2>(mapA, mapB, a, st);
         }
     }
     switch (n_tile) {
-        case 16: return launch_patch<16, 1>(mapA, mapB, a, d.B, st);
-        case 32: return launch_patch<32, 1>(mapA, mapB, a, d.B, st);
-        case 64: return launch_patch<64, 1>(mapA, mapB, a, d.B, st);
-        default: return launch_patch<128, 1>(mapA, mapB, a, d.B, st);
+        case 16: return launch_patch<16, 1>(mapA, mapB, a, st);
+        case 32: return launch_patch<32, 1>(mapA, mapB, a, st);
+        case 64: return launch_patch<64, 1>(mapA, mapB, a, st);
+        default: return launch_patch<128, 1>(mapA, mapB, a, st);
     }
 }
 

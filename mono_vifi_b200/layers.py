@@ -11,6 +11,8 @@ import torch.nn.functional as F
 
 from . import _lib
 from .fused import _prep, _ptr, workspace
+from . import conv as conv_mod
+from . import decoder_ops
 from .conv import Conv2d
 
 
@@ -98,7 +100,19 @@ class ConvBlock(nn.Module):
         self.nonlin = nn.ELU()
 
     def forward(self, x):
+        if self.conv.fast_path(x):
+            return self.conv.forward_padded(decoder_ops.upcat_pad(x), act="elu")
         return self.nonlin(self.conv(x))
+
+    def forward_upcat(self, x, skip=None, upsample=True):
+        """ConvBlock(cat([upsample(x), skip], 1)) with the upsample + concat + reflection pad done in one kernel
+        (what monodepth2.py:86-93 feeds to upconv(i,1))."""
+        if self.conv.fast_path(x) and decoder_ops.usable(x, skip, upsample):
+            return self.conv.forward_padded(decoder_ops.upcat_pad(x, skip, upsample), act="elu")
+        x = upsample_fn(x) if upsample else x
+        if skip is not None:
+            x = torch.cat([x, skip], 1)
+        return self.forward(x)
 
 
 class Conv3x3(nn.Module):
@@ -109,7 +123,17 @@ class Conv3x3(nn.Module):
         self.pad = nn.ReflectionPad2d(1) if use_refl else nn.ZeroPad2d(1)
         self.conv = Conv2d(int(in_channels), int(out_channels), 3)
 
+    def fast_path(self, x):
+        """channels-last fused pad (+ tcgen05 convolution with the activation in its epilogue)"""
+        return (x.is_cuda and isinstance(self.pad, nn.ReflectionPad2d) and conv_mod.get_backend() == "tcgen05"
+                and decoder_ops.usable(x))
+
+    def forward_padded(self, xpad, act=None):
+        return conv_mod.conv2d(xpad, self.conv.weight, self.conv.bias, 1, 0, act=act)
+
     def forward(self, x):
+        if self.fast_path(x):
+            return self.forward_padded(decoder_ops.upcat_pad(x))
         return self.conv(self.pad(x))
 
 
@@ -221,6 +245,10 @@ class Project3D(nn.Module):
     def forward(self, points, K, T):
         P = matmul_KT(K, T)[:, :3, :]
         return _Project.apply(points, P, self.batch_size, self.height, self.width, float(self.eps))
+
+
+def upsample_fn(x):
+    return F.interpolate(x, scale_factor=2, mode="nearest")
 
 
 def upsample(x, scale_factor=2, mode="nearest"):

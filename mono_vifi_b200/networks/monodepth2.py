@@ -64,11 +64,9 @@ class DepthDecoder(nn.Module):
         x = input_features[-1]
         for i in range(4, -1, -1):
             x = self.convs[("upconv", i, 0)](x)
-            x = [upsample(x)]
-            if self.use_skips and i > 0:
-                x = x + [input_features[i - 1]]
-            x = torch.cat(x, 1)
-            x = self.convs[("upconv", i, 1)](x)
+            skip = input_features[i - 1] if (self.use_skips and i > 0) else None
+            # upsample + concat + (the ConvBlock's) reflection pad in one pass, then conv + ELU  (monodepth2.py:86-93)
+            x = self.convs[("upconv", i, 1)].forward_upcat(x, skip, upsample=True)
             if i in self.scales:
                 self.outputs[("disp", i)] = self.sigmoid(self.convs[("dispconv", i)](x))
         return self.outputs

@@ -1,7 +1,7 @@
 """Per-source-line summary of an ncu report: joins the SASS page of `ncu --page source --csv` (stall samples,
 instructions executed) with nvdisasm's line table of the same kernel, in instruction order.
 
-  python tools/ncu_lines.py <report.ncu-rep> <kernel regex> <cubin> [top N]
+  python tools/ncu_lines.py <report.ncu-rep> <kernel regex> <cubin> [top N] [section regex, e.g. kernelILi64E]
 
 The cubin is the one inside the shipped .so: `cuobjdump -xelf all mono_vifi_b200/libmonovifi_b200.so`.
 """
@@ -53,13 +53,14 @@ def line_table(cubin, kernel):
 def main():
     rep, kernel, cubin = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    section = sys.argv[5] if len(sys.argv) > 5 else kernel  # regex on the mangled .text section name (template instance)
     launches = sass_rows(rep, kernel)
     if not launches:
         raise SystemExit("no kernel matching %r in %s" % (kernel, rep))
     L = launches[0]
     hdr = L["hdr"]
     si, ii, so = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Source")
-    table = line_table(cubin, kernel)
+    table = line_table(cubin, section)
     if len(table) != len(L["rows"]):
         sys.stderr.write("warning: %d SASS rows in the report, %d in the cubin\n" % (len(L["rows"]), len(table)))
     agg = collections.defaultdict(lambda: [0, 0, 0])
