@@ -228,12 +228,16 @@ static mvf::tc::ConvDesc to_desc(const mvf_conv2d_desc* d) {
 }
 int mvf_selftest_umma(const float* A, const float* B, float* D, int N, int K, int a_mn_major, void* stream) {
     if (!A || !B || !D || N < 16 || N > 256 || N % 16 || K < 32 || K % 32) return fail(MVF_ERR_INVALID, "mvf_selftest_umma: bad argument");
+    if (a_mn_major) return fail(MVF_ERR_INVALID, "mvf_selftest_umma: use mvf_selftest_umma_rows(mode 2) for the MN-major operand");
     MVF_RUN("mvf_selftest_umma", mvf::tc::umma_selftest(A, B, D, N, K, a_mn_major, (cudaStream_t)stream));
 }
 int mvf_selftest_umma_rows(const float* A, const float* B, float* D, int N, int K, int row_off, int base_off_mode, void* stream) {
-    if (!A || !B || !D || N < 16 || N > 256 || N % 16 || K < 32 || K % 32 || row_off < 0 || row_off > 32)
+    // base_off_mode: 0 / 1 = K-major A with rows shifted (descriptor base-offset field clear / set);
+    //                2 = MN-major A ([K+8][128]) with the k-rows shifted by row_off (<= 8)
+    if (!A || !B || !D || N < 16 || N > 256 || N % 16 || K < 32 || K % 32 || row_off < 0 || row_off > 32 || (base_off_mode == 2 && row_off > 8))
         return fail(MVF_ERR_INVALID, "mvf_selftest_umma_rows: bad argument");
-    MVF_RUN("mvf_selftest_umma_rows", mvf::tc::umma_selftest(A, B, D, N, K, 0, (cudaStream_t)stream, row_off, base_off_mode));
+    MVF_RUN("mvf_selftest_umma_rows", mvf::tc::umma_selftest(A, B, D, N, K, base_off_mode == 2 ? 1 : 0, (cudaStream_t)stream, row_off,
+                                                             base_off_mode == 2 ? 0 : base_off_mode));
 }
 void mvf_conv2d_debug_buffer(float* p) { mvf::tc::set_debug_buffer(p); }
 int mvf_conv2d_supported(const mvf_conv2d_desc* d) {

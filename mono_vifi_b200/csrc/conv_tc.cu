@@ -210,7 +210,8 @@ struct PatchArgs {
     int n_cblk, act;
     int patch_bytes, patch_stride;  // bytes landed per patch, distance between the two patch buffers (1024-aligned)
     int n_mtiles, n_tiles;       // M tiles (B * nseg * tiles_y), all tiles (M tiles x N tiles)
-    int dbg;                     // timing experiments only: 4 = no MMAs, 8 = no TMA loads, 16 = no stores, 32 = no epilogue
+    int tma_store;               // 1: epilogue stages slabs in shared memory and stores them with TMA; 0: per-thread stores
+    int dbg;                     // timing experiments only: 4 = no MMAs, 8 = no TMA loads
 };
 
 // Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA producer runs ahead across
@@ -218,14 +219,18 @@ struct PatchArgs {
 // buffers in TMEM, and the four epilogue warps drain one buffer while the next tile is being multiplied.
 template <int N_TILE, int MT, int NB>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                 const __grid_constant__ CUtensorMap mapB, const PatchArgs p) {
+                                                                 const __grid_constant__ CUtensorMap mapB,
+                                                                 const __grid_constant__ CUtensorMap mapY, const PatchArgs p) {
     constexpr int B_STAGE_BYTES = N_TILE * BLOCK_K * 4;
     constexpr int ACC_COLS = MT * N_TILE;  // one accumulator buffer
     constexpr int TMEM_COLS = (2 * ACC_COLS) < 32 ? 32 : (2 * ACC_COLS);
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int SLAB = N_TILE < 32 ? N_TILE : 32;      // output channels per staged slab (one TMA-store box row = SLAB floats)
+    constexpr int STAGE_OUT_BYTES = TILE_M * SLAB * 4;   // 16 KB (8 KB for 16-channel tiles)
     unsigned char* smB = smem;
-    unsigned char* smA = smem + NB * B_STAGE_BYTES;
+    unsigned char* smO = smem + NB * B_STAGE_BYTES;      // two output staging buffers
+    unsigned char* smA = smO + 2 * STAGE_OUT_BYTES;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smA + 2 * p.patch_stride);
     uint64_t* a_empty = a_full + 2;
     uint64_t* b_full = a_empty + 2;
@@ -338,11 +343,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
         }
     } else {
         // ===== epilogue: warps 2..5 own the TMEM lane quarter (warp % 4); one thread = one patch position =====
+        // TMEM -> registers -> bias / activation -> swizzled shared-memory slab [128 positions][SLAB channels] -> one TMA
+        // store per output row of the tile (the TMA unit clips rows / columns outside the image and the padding columns
+        // are simply not part of the box), so global memory sees full 128-byte lines instead of per-thread fragments.
         const int q = warp & 3;
         const int mrow = q * 32 + lane;
+        const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
         const int r = mrow / p.P, j = mrow - r * p.P;
-        constexpr int CH = (N_TILE >= 32) ? 32 : 16;
-        int acc = 0, accph = 0;
+        const bool use_tma = p.tma_store != 0;
+        int acc = 0, accph = 0, sb = 0;
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
             const int m = t % p.n_mtiles, nt = t / p.n_mtiles;
             const int seg = m % p.nseg, ty = (m / p.nseg) % p.tiles_y, b = m / (p.nseg * p.tiles_y);
@@ -351,22 +360,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
             tc_fence_after();
 #pragma unroll 1
             for (int mt = 0; mt < MT; ++mt) {
-                if (p.dbg & 32) break;
                 const int oy = ys + mt * p.TR + r, ox = xs + j;
-                const bool pix_ok = (r < p.TR) && (j < p.PWo) && (oy < p.Ho) && (ox < p.Wo) && !(p.dbg & 16);
+                const bool pix_ok = (r < p.TR) && (j < p.PWo) && (oy < p.Ho) && (ox < p.Wo);
                 float* ypix = p.y + (long long)b * p.y_sB + (long long)oy * p.y_sH + (long long)ox * p.y_sW;
-                const bool vec_ok = ((p.Cout & 3) == 0) && ((reinterpret_cast<uintptr_t>(ypix) & 15) == 0);
 #pragma unroll 1
-                for (int c0 = 0; c0 < N_TILE; c0 += CH) {
-                    uint32_t rr[CH];
+                for (int c0 = 0; c0 < N_TILE; c0 += SLAB) {
+                    uint32_t rr[SLAB];
                     const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + mt * N_TILE + c0);
-                    if constexpr (CH == 32) tmem_ld32(taddr, rr);
+                    if constexpr (SLAB == 32) tmem_ld32(taddr, rr);
                     else tmem_ld16(taddr, rr);
                     tmem_ld_wait();
-                    if (!pix_ok) continue;
-                    float v[CH];
+                    if (n0 + c0 >= p.Cout) continue;  // (uniform) slab entirely past Cout
+                    float v[SLAB];
 #pragma unroll
-                    for (int jj = 0; jj < CH; ++jj) {
+                    for (int jj = 0; jj < SLAB; ++jj) {
                         const int n = n0 + c0 + jj;
                         float tval = __uint_as_float(rr[jj]);
                         if (p.bias && n < p.Cout) tval += __ldg(p.bias + n);
@@ -374,15 +381,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
                         else if (p.act == 2) tval = tval > 0.f ? tval : expm1f(tval);
                         v[jj] = tval;
                     }
-                    if (vec_ok) {
+                    if (use_tma) {
+                        // the staging buffer must have been read by the TMA store issued two slabs ago
+                        if (et == 0) tma_store_wait_read<1>();
+                        named_barrier_sync(1, 128);
+                        unsigned char* row = smO + sb * STAGE_OUT_BYTES + mrow * (SLAB * 4);
 #pragma unroll
-                        for (int jj = 0; jj < CH; jj += 4)
-                            if (n0 + c0 + jj < p.Cout)
-                                *reinterpret_cast<float4*>(ypix + n0 + c0 + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
-                    } else {
+                        for (int k = 0; k < SLAB / 4; ++k) {
+                            // 128B (64B) swizzle on absolute address bits, as the TMA store expects
+                            const int kk = (SLAB == 32) ? (k ^ (mrow & 7)) : (k ^ ((mrow >> 1) & 3));
+                            *reinterpret_cast<float4*>(row + kk * 16) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                        }
+                        fence_proxy_async();
+                        named_barrier_sync(1, 128);
+                        if (et == 0) {
+                            for (int rrow = 0; rrow < p.TR; ++rrow) {
+                                const int oyr = ys + mt * p.TR + rrow;
+                                if (oyr < p.Ho)
+                                    tma_store_4d(&mapY, smO + sb * STAGE_OUT_BYTES + rrow * p.P * (SLAB * 4), n0 + c0, xs, oyr, b);
+                            }
+                            tma_store_commit();
+                        }
+                        sb ^= 1;
+                    } else if (pix_ok) {
+                        if (((p.Cout & 3) == 0) && ((reinterpret_cast<uintptr_t>(ypix) & 15) == 0)) {
 #pragma unroll
-                        for (int jj = 0; jj < CH; ++jj)
-                            if (n0 + c0 + jj < p.Cout) ypix[n0 + c0 + jj] = v[jj];
+                            for (int jj = 0; jj < SLAB; jj += 4)
+                                if (n0 + c0 + jj < p.Cout)
+                                    *reinterpret_cast<float4*>(ypix + n0 + c0 + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < SLAB; ++jj)
+                                if (n0 + c0 + jj < p.Cout) ypix[n0 + c0 + jj] = v[jj];
+                        }
                     }
                 }
             }
@@ -390,6 +421,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
             mbar_arrive(&acc_empty[acc]);  // this thread's TMEM reads of the buffer are complete
             if (++acc == 2) { acc = 0; accph ^= 1; }
         }
+        if (use_tma && et == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -462,9 +494,10 @@ cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const ConvA
 }
 
 template <int N_TILE, int MT>
-cudaError_t launch_patch(const CUtensorMap& mapA, const CUtensorMap& mapB, const PatchArgs& a, cudaStream_t st) {
-    constexpr int NB = (N_TILE >= 128) ? 6 : 8;  // 96 KB / 64 KB / 32 KB / 16 KB of filter tiles in flight
-    const int smem = NB * N_TILE * BLOCK_K * 4 + 2 * a.patch_stride + 1024 + 256;
+cudaError_t launch_patch(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapY, const PatchArgs& a,
+                         cudaStream_t st) {
+    constexpr int NB = (N_TILE >= 128) ? 4 : 8;  // 64 KB / 64 KB / 32 KB / 16 KB of filter tiles in flight
+    const int smem = NB * N_TILE * BLOCK_K * 4 + 2 * TILE_M * (N_TILE < 32 ? N_TILE : 32) * 4 + 2 * a.patch_stride + 1024 + 256;
     static int attr_max = 0;
     if (smem > attr_max) {
         cudaError_t e = cudaFuncSetAttribute(conv_patch_kernel<N_TILE, MT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -479,7 +512,7 @@ cudaError_t launch_patch(const CUtensorMap& mapA, const CUtensorMap& mapB, const
         if (n_sm <= 0) n_sm = 148;
     }
     const int grid = a.n_tiles < n_sm ? a.n_tiles : n_sm;
-    conv_patch_kernel<N_TILE, MT, NB><<<grid, NTHREADS, smem, st>>>(mapA, mapB, a);
+    conv_patch_kernel<N_TILE, MT, NB><<<grid, NTHREADS, smem, st>>>(mapA, mapB, mapY, a);
     return cudaGetLastError();
 }
 
@@ -558,7 +591,8 @@ static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const f
     a.dbg = getenv("MVF_CONV_DBG") ? atoi(getenv("MVF_CONV_DBG")) : 0;
     a.n_mtiles = d.B * a.nseg * a.tiles_y;
     a.n_tiles = a.n_mtiles * n_ntiles;
-    if ((n_tile >= 128 ? 6 : 8) * n_tile * BLOCK_K * 4 + 2 * a.patch_stride + 1280 > 227 * 1024) {
+    const int slab = n_tile < 32 ? n_tile : 32;
+    if ((n_tile >= 128 ? 4 : 8) * n_tile * BLOCK_K * 4 + 2 * TILE_M * slab * 4 + 2 * a.patch_stride + 1280 > 227 * 1024) {
         *why = "patch does not fit in shared memory";
         return cudaErrorInvalidValue;
     }
@@ -587,19 +621,38 @@ static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const f
             return cudaErrorInvalidValue;
         }
     }
+    // output as (c, x, y, b) for the TMA-store epilogue: one box = one output row of a tile, SLAB channels wide
+    CUtensorMap mapY;
+    // (16-channel tiles would need 64-byte staging rows, which the TMA store cannot address at odd row offsets)
+    a.tma_store = (n_tile >= 32 && (d.Cout % 4) == 0 && (d.y_sW % 4) == 0 && (d.y_sH % 4) == 0 && (d.y_sB % 4) == 0 && (((uintptr_t)y) & 15) == 0 &&
+                   !getenv("MVF_CONV_NO_TMA_STORE")) ? 1 : 0;
+    if (a.tma_store) {
+        cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)d.y_sW * 4, (cuuint64_t)d.y_sH * 4, (cuuint64_t)d.y_sB * 4};
+        cuuint32_t box[4] = {(cuuint32_t)slab, (cuuint32_t)a.PWo, 1, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        if (enc(&mapY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                slab == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            *why = "cuTensorMapEncodeTiled failed for the output tensor";
+            return cudaErrorInvalidValue;
+        }
+    } else {
+        mapY = mapA;  // unused by the kernel
+    }
     if (MT == 2) {
         switch (n_tile) {
-            case 16: return launch_patch<16, 2>(mapA, mapB, a, st);
-            case 32: return launch_patch<32, 2>(mapA, mapB, a, st);
-            case 64: return launch_patch<64, 2>(mapA, mapB, a, st);
-            default: return launch_patch<128, 2>(mapA, mapB, a, st);
+            case 16: return launch_patch<16, 2>(mapA, mapB, mapY, a, st);
+            case 32: return launch_patch<32, 2>(mapA, mapB, mapY, a, st);
+            case 64: return launch_patch<64, 2>(mapA, mapB, mapY, a, st);
+            default: return launch_patch<128, 2>(mapA, mapB, mapY, a, st);
         }
     }
     switch (n_tile) {
-        case 16: return launch_patch<16, 1>(mapA, mapB, a, st);
-        case 32: return launch_patch<32, 1>(mapA, mapB, a, st);
-        case 64: return launch_patch<64, 1>(mapA, mapB, a, st);
-        default: return launch_patch<128, 1>(mapA, mapB, a, st);
+        case 16: return launch_patch<16, 1>(mapA, mapB, mapY, a, st);
+        case 32: return launch_patch<32, 1>(mapA, mapB, mapY, a, st);
+        case 64: return launch_patch<64, 1>(mapA, mapB, mapY, a, st);
+        default: return launch_patch<128, 1>(mapA, mapB, mapY, a, st);
     }
 }
 

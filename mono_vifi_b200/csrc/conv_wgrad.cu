@@ -25,31 +25,34 @@ constexpr int M_TILE = 128;  // couts per CTA (UMMA M)
 constexpr int N_TILE = 32;   // cins per CTA (UMMA N), one 128-byte MN atom
 constexpr int KP = 32;       // pixels per pipeline stage (4 MMAs of K = 8 per tap)
 constexpr int MAX_TAPS = 9;  // taps x 32 columns <= 512 TMEM columns, 4 stages of (16 + 4 taps) KB of shared memory
-constexpr int A_BYTES = M_TILE * KP * 4;      // 16 KB
-constexpr int B_TAP_BYTES = N_TILE * KP * 4;  // 4 KB
 constexpr int NTHREADS = 192;
 
 struct WgradArgs {
     float* partial;  // [ksplit][taps][Cout_pad128][Cin_pad32]
     int Cout, Cin, KH, KW, pad, stride;
     int Ho, Wo, B;
-    int pw_log2;     // pixel patch = (1 << pw_log2) x (32 >> pw_log2) output pixels
+    int pw, ph;      // pixel patch of one pipeline stage: pw x ph output pixels (pw * ph a multiple of 8, <= 64)
     int patches_x, patches_y;
     int n_patches;   // B * patches_y * patches_x
     int ksplit;
     int cout_pad, cin_pad;
+    int shared_patch;  // 1 (stride 1, ph == 1): ONE haloed x patch per stage serves all taps; 0: one x box per tap
+    int pwx;           // shared patch: its pitch in pixels (pw + KW - 1)
+    int stage_bytes, a_bytes, b_bytes;  // stage stride (1024-aligned), bytes landed for A and for B (all taps)
+    int stages;        // pipeline depth (2..6), as many as fit in shared memory
 };
 
-template <int STAGES>
+constexpr int MAX_STAGES = 6;
+
 __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapG,
                                                               const __grid_constant__ CUtensorMap mapX, const WgradArgs p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int taps = p.KH * p.KW;
-    const int stage_bytes = A_BYTES + taps * B_TAP_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    const int STAGES = p.stages;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * p.stage_bytes);
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
     const int per = (p.n_patches + p.ksplit - 1) / p.ksplit;
     const int k_begin = split * per, k_end = min(p.n_patches, k_begin + per);
     const int n_iters = max(0, k_end - k_begin);
-    const int PW = 1 << p.pw_log2, PH = KP >> p.pw_log2;
+    const int kp = p.pw * p.ph;  // pixels per stage
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapG);
@@ -81,48 +84,63 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
 
     if (warp == 0) {
         if (lane == 0) {
+            int s = 0, ph = 0;
+            int px = k_begin % p.patches_x, py = (k_begin / p.patches_x) % p.patches_y, b = k_begin / (p.patches_x * p.patches_y);
             for (int it = 0; it < n_iters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
-                const int k = k_begin + it;
-                const int px = k % p.patches_x, py = (k / p.patches_x) % p.patches_y, b = k / (p.patches_x * p.patches_y);
-                const int ox0 = px * PW, oy0 = py * PH;
-                unsigned char* st = smem + s * stage_bytes;
-                mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-                // A: gy as (co%32, ox, oy, b, co/32), box (32, PW, PH, 1, 4) -> smem [co/32][pixel][32 co]
+                const int ox0 = px * p.pw, oy0 = py * p.ph;
+                unsigned char* st = smem + s * p.stage_bytes;
+                mbar_arrive_expect_tx(&full_bar[s], p.a_bytes + p.b_bytes);
+                // A: gy as (co%32, ox, oy, b, co/32), box (32, pw, ph, 1, 4) -> smem [co/32][pixel][32 co]
                 tma_load_5d(st, &mapG, &full_bar[s], 0, ox0, oy0, b, co0 / 32);
-                // B_t: x as (ci, ix, iy, b), box (32, PW*s, PH*s, 1) walked with the conv stride -> smem [pixel][32 ci]
-                for (int t = 0; t < taps; ++t) {
-                    const int kh = t / p.KW, kw = t - kh * p.KW;
-                    tma_load_4d(st + A_BYTES + t * B_TAP_BYTES, &mapX, &full_bar[s], ci0, ox0 * p.stride + kw - p.pad,
-                                oy0 * p.stride + kh - p.pad, b);
+                if (p.shared_patch) {
+                    // x as (ci, ix, iy, b), box (32, pw + KW - 1, KH, 1): the haloed patch all taps read
+                    tma_load_4d(st + p.a_bytes, &mapX, &full_bar[s], ci0, ox0 - p.pad, oy0 - p.pad, b);
+                } else {
+                    // one box per tap, walked with the convolution stride -> smem [tap][pixel][32 ci]
+                    int kh = 0, kw = 0;
+                    for (int t = 0; t < taps; ++t) {
+                        tma_load_4d(st + p.a_bytes + t * (kp * 128), &mapX, &full_bar[s], ci0, ox0 * p.stride + kw - p.pad,
+                                    oy0 * p.stride + kh - p.pad, b);
+                        if (++kw == p.KW) { kw = 0; ++kh; }
+                    }
                 }
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+                if (++px == p.patches_x) { px = 0; if (++py == p.patches_y) { py = 0; ++b; } }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(M_TILE, N_TILE, /*A MN-major*/ 1, /*B MN-major*/ 1);
-            for (int it = 0; it < n_iters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
-                tc_fence_after();
-                const uint32_t a_base = smem_u32(smem + s * stage_bytes), b_base = a_base + A_BYTES;
+        // the whole warp runs the (uniform) loop; one elected lane issues
+        constexpr uint32_t idesc = make_idesc_tf32(M_TILE, N_TILE, /*A MN-major*/ 1, /*B MN-major*/ 1);
+        // MN-major, 32-byte-unit 128B swizzle: 512-byte atoms of (4 pixels x 32 channels); the next 4 pixels +512 B (SBO),
+        // the next 32 couts +kp*128 B (LBO, A only: B is one atom wide)
+        const uint64_t a_hi = make_smem_desc(0, kp * 128, 512, SWZ_128B_BASE32B);
+        const uint64_t b_hi = make_smem_desc(0, 512, 512, SWZ_128B_BASE32B);
+        const uint32_t smem_u = smem_u32(smem);
+        const int kmma = kp / 8;
+        int s = 0, ph = 0;
+        for (int it = 0; it < n_iters; ++it) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_lo = (smem_u + (uint32_t)(s * p.stage_bytes)) >> 4;
+            const uint32_t b_lo = a_lo + ((uint32_t)p.a_bytes >> 4);
+            if (elect_one()) {
+                int kh = 0, kw = 0;
                 for (int t = 0; t < taps; ++t) {
-#pragma unroll
-                    for (int kk = 0; kk < KP / 8; ++kk) {
-                        // MN-major, 32-byte-unit 128B swizzle: 512-byte atoms of (4 pixels x 32 channels); the next 4 pixels
-                        // +512 B (SBO), the next 32 couts +KP*128 B (LBO); this MMA's 8 pixels start kk*1024 B in
-                        const uint64_t adesc = make_smem_desc(a_base + kk * 1024, KP * 128, 512, SWZ_128B_BASE32B);
-                        const uint64_t bdesc = make_smem_desc(b_base + t * B_TAP_BYTES + kk * 1024, KP * 128, 512, SWZ_128B_BASE32B);
-                        umma_tf32(tmem_d + (uint32_t)(t * N_TILE), adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-                    }
+                    // tap t: its own box, or the shared patch shifted by kh rows and kw pixels (whole 128-byte rows)
+                    const uint32_t bt = p.shared_patch ? b_lo + (uint32_t)((kh * p.pwx + kw) * 8) : b_lo + (uint32_t)(t * kp * 8);
+                    for (int kk = 0; kk < kmma; ++kk)
+                        umma_tf32(tmem_d + (uint32_t)(t * N_TILE), a_hi | (uint64_t)(a_lo + kk * 64), b_hi | (uint64_t)(bt + kk * 64),
+                                  idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                    if (++kw == p.KW) { kw = 0; ++kh; }
                 }
                 umma_commit(&empty_bar[s]);
             }
-            umma_commit(tmem_full_bar);
+            __syncwarp();
+            if (++s == STAGES) { s = 0; ph ^= 1; }
         }
+        if (elect_one()) umma_commit(tmem_full_bar);
+        __syncwarp();
     } else {
         // epilogue: thread = one cout row; per tap 32 contiguous cins
         const int q = warp & 3;
@@ -156,19 +174,29 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
     }
 }
 
-// dw[co][ci][tap] = sum over splits (fixed order) of partial[split][tap][co][ci]
+// dw[co][ci][tap] = sum over splits (fixed order) of partial[split][tap][co][ci]; one thread = 4 consecutive cins
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin, int taps,
                                     int ksplit, int cout_pad, int cin_pad) {
-    const long long total = (long long)Cout * Cin * taps;
+    const int cin4 = (Cin + 3) / 4;
+    const long long total = (long long)Cout * taps * cin4;
+    const size_t split_stride = (size_t)taps * cout_pad * cin_pad;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        // consecutive threads walk ci fastest so that the partial reads coalesce
-        const int ci = (int)(i % Cin);
-        long long r = i / Cin;
+        const int c4 = (int)(i % cin4);
+        long long r = i / cin4;
         const int t = (int)(r % taps);
         const int co = (int)(r / taps);
-        float acc = 0.f;
-        for (int s = 0; s < ksplit; ++s) acc += partial[(((size_t)s * taps + t) * cout_pad + co) * cin_pad + ci];
-        dw[((long long)co * Cin + ci) * taps + t] = acc;
+        const float4* src = reinterpret_cast<const float4*>(partial + ((size_t)t * cout_pad + co) * cin_pad + 4 * c4);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < ksplit; ++s) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + s * split_stride));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        const int ci = 4 * c4;
+        float* o = dw + ((long long)co * Cin + ci) * taps + t;
+        o[0] = acc.x;
+        if (ci + 1 < Cin) o[taps] = acc.y;
+        if (ci + 2 < Cin) o[2 * taps] = acc.z;
+        if (ci + 3 < Cin) o[3 * taps] = acc.w;
     }
 }
 
@@ -191,27 +219,52 @@ EncodeTiledFn wgrad_encode_fn() {
 int out_size(int n, int k, int pad, int stride) { return (n + 2 * pad - k) / stride + 1; }
 
 struct Plan {
-    int Ho, Wo, pw_log2, patches_x, patches_y, n_patches, ksplit, cout_pad, cin_pad, stages;
+    int Ho, Wo, pw, ph, patches_x, patches_y, n_patches, ksplit, cout_pad, cin_pad, stages;
+    int shared_patch, pwx, a_bytes, b_bytes, stage_bytes;
 };
 
 Plan make_plan(const WgradDesc& d) {
     Plan pl;
     pl.Ho = out_size(d.H, d.KH, d.pad, d.stride);
     pl.Wo = out_size(d.W, d.KW, d.pad, d.stride);
-    int best = 5;
-    long long best_cost = -1;
-    for (int j = 5; j >= 0; --j) {
-        const int pw = 1 << j, ph = KP >> j;
-        const long long cost = (long long)((pl.Wo + pw - 1) / pw) * ((pl.Ho + ph - 1) / ph);
-        if (best_cost < 0 || cost < best_cost) {
-            best_cost = cost;
-            best = j;
+    const int taps = d.KH * d.KW;
+    pl.shared_patch = (d.stride == 1 && taps > 1 && !getenv("MVF_WGRAD_NO_PATCH")) ? 1 : 0;
+    if (pl.shared_patch) {
+        // one output-row segment of pw pixels per stage (pw a multiple of 8, <= 64): least padding, then the widest
+        int best = 32;
+        long long best_cost = -1;
+        for (int pw = 64; pw >= 8; pw -= 8) {
+            const long long cost = (long long)((pl.Wo + pw - 1) / pw) * pw;
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                best = pw;
+            }
         }
+        pl.pw = best;
+        pl.ph = 1;
+        pl.pwx = pl.pw + d.KW - 1;
+        pl.b_bytes = d.KH * pl.pwx * 128;
+    } else {
+        int best = 5;
+        long long best_cost = -1;
+        for (int j = 5; j >= 0; --j) {
+            const int pw = 1 << j, ph = KP >> j;
+            const long long cost = (long long)((pl.Wo + pw - 1) / pw) * ((pl.Ho + ph - 1) / ph);
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                best = j;
+            }
+        }
+        pl.pw = 1 << best;
+        pl.ph = KP >> best;
+        pl.pwx = 0;
+        pl.b_bytes = taps * pl.pw * pl.ph * 128;
     }
-    pl.pw_log2 = best;
-    pl.patches_x = (pl.Wo + (1 << best) - 1) >> best;
-    const int ph = KP >> best;
-    pl.patches_y = (pl.Ho + ph - 1) / ph;
+    pl.a_bytes = pl.pw * pl.ph * 128 * 4;
+    // the MMAs of the last taps of a shared patch read up to KW - 1 rows past it: keep them inside the stage
+    pl.stage_bytes = (pl.a_bytes + pl.b_bytes + (pl.shared_patch ? (d.KW - 1) * 128 : 0) + 1023) / 1024 * 1024;
+    pl.patches_x = (pl.Wo + pl.pw - 1) / pl.pw;
+    pl.patches_y = (pl.Ho + pl.ph - 1) / pl.ph;
     pl.n_patches = d.B * pl.patches_x * pl.patches_y;
     pl.cout_pad = (d.Cout + M_TILE - 1) / M_TILE * M_TILE;
     pl.cin_pad = (d.Cin + N_TILE - 1) / N_TILE * N_TILE;
@@ -222,7 +275,9 @@ Plan make_plan(const WgradDesc& d) {
     if (ks > max_ks) ks = max_ks;
     if (ks < 1) ks = 1;
     pl.ksplit = ks;
-    pl.stages = 4;
+    pl.stages = (224 * 1024) / pl.stage_bytes;
+    if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;
+    if (pl.stages < 2) pl.stages = 2;
     return pl;
 }
 
@@ -258,12 +313,14 @@ cudaError_t conv_wgrad(const WgradDesc& d, const float* x, const float* gy, floa
         return cudaErrorInvalidValue;
     }
     const Plan pl = make_plan(d);
-    const int PW = 1 << pl.pw_log2, PH = KP >> pl.pw_log2;
+    const int PW = pl.pw, PH = pl.ph;
     WgradArgs a;
     a.partial = workspace;
     a.Cout = d.Cout; a.Cin = d.Cin; a.KH = d.KH; a.KW = d.KW; a.pad = d.pad; a.stride = d.stride;
     a.Ho = pl.Ho; a.Wo = pl.Wo; a.B = d.B;
-    a.pw_log2 = pl.pw_log2; a.patches_x = pl.patches_x; a.patches_y = pl.patches_y; a.n_patches = pl.n_patches;
+    a.pw = pl.pw; a.ph = pl.ph; a.patches_x = pl.patches_x; a.patches_y = pl.patches_y; a.n_patches = pl.n_patches;
+    a.stages = pl.stages;
+    a.shared_patch = pl.shared_patch; a.pwx = pl.pwx; a.stage_bytes = pl.stage_bytes; a.a_bytes = pl.a_bytes; a.b_bytes = pl.b_bytes;
     a.ksplit = pl.ksplit; a.cout_pad = pl.cout_pad; a.cin_pad = pl.cin_pad;
 
     CUtensorMap mapG, mapX;
@@ -285,6 +342,10 @@ cudaError_t conv_wgrad(const WgradDesc& d, const float* x, const float* gy, floa
         cuuint64_t strides[3] = {(cuuint64_t)d.x_sW * 4, (cuuint64_t)d.x_sH * 4, (cuuint64_t)d.x_sB * 4};
         cuuint32_t box[4] = {32, (cuuint32_t)(PW * d.stride), (cuuint32_t)(PH * d.stride), 1};
         cuuint32_t es[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
+        if (pl.shared_patch) {
+            box[1] = (cuuint32_t)pl.pwx;
+            box[2] = (cuuint32_t)d.KH;
+        }
         if (enc(&mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, es,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
@@ -293,21 +354,19 @@ cudaError_t conv_wgrad(const WgradDesc& d, const float* x, const float* gy, floa
         }
     }
     const int taps = d.KH * d.KW;
-    const int stage_bytes = A_BYTES + taps * B_TAP_BYTES;
-    const int smem = pl.stages * stage_bytes + 1024 + 256;
+    const int smem = pl.stages * pl.stage_bytes + 1024 + 256;
     dim3 grid(pl.cout_pad / M_TILE, pl.cin_pad / N_TILE, pl.ksplit);
     cudaError_t e;
     static bool attr_set = false;
     if (!attr_set) {
-        e = cudaFuncSetAttribute(conv_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 4 * (A_BYTES + MAX_TAPS * B_TAP_BYTES) + 1280);
+        e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_wgrad_kernel<4><<<grid, NTHREADS, smem, st>>>(mapG, mapX, a);
+    conv_wgrad_kernel<<<grid, NTHREADS, smem, st>>>(mapG, mapX, a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const long long total = (long long)d.Cout * d.Cin * taps;
+    const long long total = (long long)d.Cout * taps * ((d.Cin + 3) / 4);
     const int threads = 256;
     const int blocks = (int)((total + threads - 1) / threads < 1184 ? (total + threads - 1) / threads : 1184);
     wgrad_reduce_kernel<<<blocks, threads, 0, st>>>(workspace, dw, d.Cout, d.Cin, taps, pl.ksplit, pl.cout_pad, pl.cin_pad);

@@ -37,10 +37,10 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __grid_constan
     const int nkb = K / 32;
     for (int kb = 0; kb < nkb; ++kb) {
         if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(full_bar, (a_mn_major ? 16384 : 20480) + N * 128);
+            mbar_arrive_expect_tx(full_bar, 20480 + N * 128);
             if (a_mn_major) {
-                // A given as [K][128]: dims (m%32, k%8, m/32, k/8), box (32, 8, 4, 4) -> smem [k/8][m/32][k%8][m%32]
-                tma_load_4d(smA, &mapA, full_bar, 0, 0, 0, kb * 4);
+                // A given as [K+8][128]: dims (m%32, k, m/32), box (32, 40, 4) -> smem [m/32][40 k-rows][m%32]
+                tma_load_3d(smA, &mapA, full_bar, 0, kb * 32, 0);
             } else {
                 tma_load_3d(smA, &mapA, full_bar, 0, 0, kb);  // dims (k%32, m, k/32), box (32, 160, 1)
             }
@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __grid_constan
             tc_fence_after();
             for (int kg = 0; kg < 4; ++kg) {
                 uint64_t adesc, bdesc;
-                if (a_mn_major) adesc = make_smem_desc(smem_u32(smA) + kg * 4096, 1024, 512, SWZ_128B_BASE32B);
+                if (a_mn_major)  // k-rows [row_off + 8 kg, +8) of each 32-wide MN atom; atoms 40 rows (5120 B) apart
+                    adesc = make_smem_desc(smem_u32(smA) + (row_off + 8 * kg) * 128, 40 * 128, 512, SWZ_128B_BASE32B);
                 else {
                     // experiment: operand = rows [row_off, row_off + 128) of the 160 loaded rows (start not 1024-aligned)
                     const uint32_t start = smem_u32(smA) + row_off * 128 + kg * 32;
@@ -81,7 +82,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 }  // namespace
 
-// A: [160][K] of which rows [row_off, row_off+128) are used (a_mn_major = 0) or [K][128] (a_mn_major = 1); B: [N][K];
+// A: [160][K] of which rows [row_off, row_off+128) are used (a_mn_major = 0) or [K+8][128] of which k-rows
+// [row_off, row_off+K) are used (a_mn_major = 1); B: [N][K];
 // D: [128][N].  K % 32 == 0, N % 16 == 0, N <= 256.
 cudaError_t umma_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn_major, cudaStream_t st,
                           int row_off, int base_off_mode) {
@@ -93,10 +95,10 @@ cudaError_t umma_selftest(const float* A, const float* B, float* D, int N, int K
     CUtensorMap mapA, mapB;
     cuuint32_t es[4] = {1, 1, 1, 1};
     if (a_mn_major) {
-        cuuint64_t dims[4] = {32, 8, 4, (cuuint64_t)(K / 8)};
-        cuuint64_t strides[3] = {128 * 4, 32 * 4, 128 * 4 * 8};
-        cuuint32_t box[4] = {32, 8, 4, 4};
-        if (enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(A), dims, strides, box, es,
+        cuuint64_t dims[4] = {32, (cuuint64_t)(K + 8), 4, 1};
+        cuuint64_t strides[3] = {128 * 4, 32 * 4, 128 * 4};
+        cuuint32_t box[4] = {32, 40, 4, 1};
+        if (enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(A), dims, strides, box, es,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;

@@ -109,17 +109,26 @@ def test_umma_selftest_pins_descriptors():
     import torch
     from mono_vifi_b200 import _lib
     L = _lib.lib()
-    for mn in (0, 1):
-        for N, K in ((16, 32), (64, 64), (256, 96)):
-            g = torch.Generator(device="cuda").manual_seed(1)
-            A = torch.randn(128, K, device="cuda", generator=g)
-            Bm = torch.randn(N, K, device="cuda", generator=g)
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for N, K in ((16, 32), (64, 64), (256, 96)):
+        # K-major A [160][K]; rows [off, off+128) are the operand (off != 0: start not aligned to the swizzle pattern)
+        A = torch.randn(160, K, device="cuda", generator=g)
+        Bm = torch.randn(N, K, device="cuda", generator=g)
+        for off in (0, 1, 5, 17):
             D = torch.full((128, N), -5.0, device="cuda")
-            Ain = A.t().contiguous() if mn else A
-            _lib.check(L.mvf_selftest_umma(Ain.data_ptr(), Bm.data_ptr(), D.data_ptr(), N, K, mn,
-                                           torch.cuda.current_stream().cuda_stream), "mvf_selftest_umma")
-            ref = A.double() @ Bm.double().t()
+            _lib.check(L.mvf_selftest_umma_rows(A.data_ptr(), Bm.data_ptr(), D.data_ptr(), N, K, off, 0, st), "mvf_selftest_umma_rows")
+            ref = A[off:off + 128].double() @ Bm.double().t()
             assert (D.double() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() * (K / 32) ** 0.5
+    # MN-major A [K+8][128] (the layout NCHW / pixel-major operands have), k-rows shifted by off
+    N, K = 64, 32
+    A = torch.randn(K + 8, 128, device="cuda", generator=g)
+    Bm = torch.randn(N, K, device="cuda", generator=g)
+    for off in (0, 1, 3, 8):
+        D = torch.full((128, N), -5.0, device="cuda")
+        _lib.check(L.mvf_selftest_umma_rows(A.data_ptr(), Bm.data_ptr(), D.data_ptr(), N, K, off, 2, st), "mvf_selftest_umma_rows")
+        ref = A[off:off + K].double().t() @ Bm.double().t()
+        assert (D.double() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
 
 
 WGRAD_CASES = [
