@@ -44,7 +44,7 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, act=
     if _backend == "tcgen05" and x.is_cuda:
         from . import conv_tc
         cin = weight.shape[1]
-        if cin % 4:
+        if cin % 4 and groups == 1:
             # image-like inputs (3 or 6 channels): zero channels up to a 16-byte pixel; autograd slices the gradient back
             extra = 4 - cin % 4
             x = F.pad(x, (0, 0, 0, 0, 0, extra))

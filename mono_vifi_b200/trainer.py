@@ -24,6 +24,12 @@ class Options:
         self.no_ssim = self.avg_reprojection = self.disable_automasking = False
         self.learning_rate, self.weight_decay, self.clip_grad = 1e-4, 0.01, 5.0
         self.num_layers = 18
+        self.num_scales = 1
+        self.backbone = "ResNet18"              # ResNet18 | ResNet50 | DHRNet | LiteMono   (options.py:187-190)
+        self.fuse_model_type = "shared_encoder"  # shared_encoder | separate_all | shared_all (options.py:196-200)
+        self.vfi_scale = "small"                # IFRNet size (options.py:191-195)
+        self.lamda = 0.2                        # weight of the depth-consistency loss (options.py:92-95)
+        self.multi_frame = False                # False: the single-frame slice (BASELINE configs[1]); True: full process_batch
         self.tie_break_noise = True  # train.py:1023: torch.randn * 1e-5 on the identity terms
         for k, v in kw.items():
             if not hasattr(self, k):
@@ -32,10 +38,31 @@ class Options:
 
 
 def build_models(opt, device):
-    """train.py:142-190 for backbone ResNet18 (weights_init=scratch)."""
+    """train.py:142-190 (weights_init=scratch): depth encoder / decoder of the chosen backbone, pose networks and, for the
+    multi-frame branch, the second decoder (or encoder + decoder) and the fusion module."""
+    import copy
     models = {}
-    models["encoder"] = N.monodepth2.DepthEncoder(opt.num_layers, False)
-    models["depth"] = N.monodepth2.DepthDecoder(models["encoder"].num_ch_enc, range(1))
+    if opt.backbone in ("ResNet18", "ResNet50"):
+        models["encoder"] = N.monodepth2.DepthEncoder(18 if opt.backbone == "ResNet18" else 50, False)
+        models["depth"] = N.monodepth2.DepthDecoder(models["encoder"].num_ch_enc, range(opt.num_scales))
+    elif opt.backbone == "DHRNet":
+        models["encoder"] = N.DHRNet.DepthEncoder(18, False)
+        models["depth"] = N.DHRNet.DepthDecoder(models["encoder"].num_ch_enc, range(opt.num_scales))
+    elif opt.backbone == "LiteMono":
+        models["encoder"] = N.LiteMono.DepthEncoder(model="lite-mono", drop_path_rate=0.2, width=opt.width, height=opt.height)
+        models["depth"] = N.LiteMono.DepthDecoder(models["encoder"].num_ch_enc, range(opt.num_scales))
+    else:
+        raise ValueError("unknown backbone %r" % (opt.backbone,))
+    if opt.multi_frame:
+        if opt.fuse_model_type == "shared_all":
+            models["encoder_mf"], models["depth_mf"] = models["encoder"], models["depth"]
+        elif opt.fuse_model_type == "shared_encoder":
+            models["encoder_mf"], models["depth_mf"] = models["encoder"], copy.deepcopy(models["depth"])
+        elif opt.fuse_model_type == "separate_all":
+            models["encoder_mf"], models["depth_mf"] = copy.deepcopy(models["encoder"]), copy.deepcopy(models["depth"])
+        else:
+            raise ValueError("unknown fuse_model_type %r" % (opt.fuse_model_type,))
+        models["fusion_module"] = N.FusionModule(opt, models["encoder_mf"].num_ch_enc)
     models["pose_encoder"] = N.posenet.ResnetEncoder(opt.num_layers, False, num_input_images=2)
     models["pose"] = N.posenet.PoseDecoder(models["pose_encoder"].num_ch_enc, num_input_features=1,
                                            num_frames_to_predict_for=2)
@@ -76,14 +103,66 @@ def single_frame_losses(models, inputs, opt):
     return {"loss": loss, "loss_base": loss, "disp": disp_0, "auto_mask": auto_mask}
 
 
+def multi_frame_losses(models, vfi, inputs, opt):
+    """The full process_batch of the reference without the affine branch (train.py:698-814, 885): three VFI passes
+    (frozen IFRNet), six pose passes, single-frame depth of the target and of the two synthesized frames, fused
+    multi-frame depth of the same three, six photometric loss groups (each ONE fused kernel launch) and three
+    scale-invariant log depth-consistency terms.  loss = loss_base + lamda * loss_dc."""
+    img_n1, img_0, img_p1 = inputs[("color", -1, 0)], inputs[("color", 0, 0)], inputs[("color", 1, 0)]
+    aug_n1, aug_0, aug_p1 = inputs[("color_aug", -1, 0)], inputs[("color_aug", 0, 0)], inputs[("color_aug", 1, 0)]
+    K, inv_K = inputs[("K", 0)], inputs[("inv_K", 0)]
+    embt = torch.full((img_0.shape[0], 1, 1, 1), 0.5, device=img_0.device)
+    with torch.no_grad():
+        img_nt, flow_nt_n1, flow_nt_0, mask_nt = vfi(img_n1, img_0, embt)
+        img_pt, flow_pt_0, flow_pt_p1, mask_pt = vfi(img_0, img_p1, embt)
+        flow_0_n1, flow_0_p1, mask_01 = vfi(img_n1, img_p1, embt, onlyFlow=True)
+    _, pose_0_n1 = predict_poses(models, aug_n1, aug_0)
+    pose_0_p1, _ = predict_poses(models, aug_0, aug_p1)
+    _, pose_nt_n1 = predict_poses(models, img_n1, img_nt)
+    pose_nt_p1, _ = predict_poses(models, img_nt, img_p1)
+    _, pose_pt_n1 = predict_poses(models, img_n1, img_pt)
+    pose_pt_p1, _ = predict_poses(models, img_pt, img_p1)
+
+    enc, dec = models["encoder"], models["depth"]
+    keep = lambda feats: list(feats)  # the reference's encoders overwrite self.features on every call
+    feats_0, feats_nt, feats_pt = keep(enc(aug_0)), keep(enc(img_nt)), keep(enc(img_pt))
+    disp_0, disp_nt, disp_pt = dec(feats_0)[("disp", 0)], dec(feats_nt)[("disp", 0)], dec(feats_pt)[("disp", 0)]
+    loss_base = 0.0
+    group = lambda disp, tgt, T_n1, T_p1: loss_group(opt, disp, tgt, T_n1, T_p1, img_n1, img_p1, K, inv_K)[0]
+    loss_base = group(disp_0, img_0, pose_0_n1, pose_0_p1) + group(disp_pt, img_pt, pose_pt_n1, pose_pt_p1) + \
+        group(disp_nt, img_nt, pose_nt_n1, pose_nt_p1)
+
+    enc_mf, dec_mf, fuse = models["encoder_mf"], models["depth_mf"], models["fusion_module"]
+    if opt.fuse_model_type == "separate_all":
+        feats_0, feats_nt, feats_pt = keep(enc_mf(aug_0)), keep(enc_mf(img_nt)), keep(enc_mf(img_pt))
+    feats_n1, feats_p1 = keep(enc_mf(aug_n1)), keep(enc_mf(aug_p1))
+    disp_0_f = dec_mf(fuse([feats_n1, feats_0, feats_p1], [flow_0_n1, flow_0_p1], mask_01))[("disp", 0)]
+    disp_nt_f = dec_mf(fuse([feats_n1, feats_nt, feats_0], [flow_nt_n1, flow_nt_0], mask_nt))[("disp", 0)]
+    disp_pt_f = dec_mf(fuse([feats_0, feats_pt, feats_p1], [flow_pt_0, flow_pt_p1], mask_pt))[("disp", 0)]
+    loss_base = loss_base + group(disp_0_f, img_0, pose_0_n1, pose_0_p1) + group(disp_nt_f, img_nt, pose_nt_n1, pose_nt_p1) + \
+        group(disp_pt_f, img_pt, pose_pt_n1, pose_pt_p1)
+    depth = lambda d: L.disp_to_depth(d, opt.min_depth, opt.max_depth)[1]
+    loss_dc = L.si_log_depth_loss(depth(disp_0), depth(disp_0_f)) + L.si_log_depth_loss(depth(disp_nt), depth(disp_nt_f)) + \
+        L.si_log_depth_loss(depth(disp_pt), depth(disp_pt_f))
+    return {"loss": loss_base + opt.lamda * loss_dc, "loss_base": loss_base, "loss_dc": loss_dc, "disp": disp_0,
+            "disp_fuse": disp_0_f}
+
+
 class TrainStep:
     """zero_grad -> forward -> backward -> (all-reduce) -> clip -> AdamW  (train.py:656-666)."""
 
     def __init__(self, opt, device, models=None, distributed=False, capturable=False):
         self.opt, self.device = opt, device
         self.models = models if models is not None else build_models(opt, device)
-        # the reference appends every model's parameters (train.py:198-200)
-        self.params = [p for m in self.models.values() for p in m.parameters()]
+        # the frozen VFI network of the multi-frame branch (train.py:210-216); not trained, not in the optimizer
+        self.vfi = N.IFRNet(opt.vfi_scale).to(device).eval() if opt.multi_frame else None
+        # the reference appends every model's parameters (train.py:198-200; shared modules appear once here)
+        seen, self.params = set(), []
+        for m in self.models.values():
+            for p in m.parameters():
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    self.params.append(p)
         # capturable: step counters live on the device so that the whole step can be recorded into a CUDA graph
         self.optimizer = torch.optim.AdamW(self.params, lr=opt.learning_rate, weight_decay=opt.weight_decay,
                                            capturable=bool(capturable and device.type == "cuda"))
@@ -102,7 +181,10 @@ class TrainStep:
             self.reducer.attach()  # zeroes the flat arena and points every .grad at its slice
         else:
             self.optimizer.zero_grad(set_to_none=True)
-        out = single_frame_losses(self.models, inputs, self.opt)
+        if self.opt.multi_frame:
+            out = multi_frame_losses(self.models, self.vfi, inputs, self.opt)
+        else:
+            out = single_frame_losses(self.models, inputs, self.opt)
         out["loss"].backward()
         if self.reducer is not None:
             self.reducer.allreduce_mean()
