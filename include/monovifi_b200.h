@@ -133,6 +133,9 @@ typedef struct {
     int Cout, KH, KW, pad, stride;  /* output [B,Cout,(H+2pad-KH)/stride+1,(W+2pad-KW)/stride+1] */
     long long x_stride[3];          /* batch, row (y), column (x) */
     long long y_stride[3];
+    int stride_x;                   /* column stride when it differs from `stride` (rows); 0 = same.  Used by the
+                                       row-packed 7x7 stem: the input is viewed as [B, 8 px * C, H+6, Wo] with an
+                                       overlapping column stride of 2 px, so the column stride of the conv is 1 */
 } mvf_conv2d_desc;
 #define MVF_ACT_NONE 0
 #define MVF_ACT_RELU 1

@@ -17,7 +17,7 @@ class F1Params(ctypes.Structure):
 class Conv2dDesc(ctypes.Structure):
     _fields_ = [("B", ctypes.c_int), ("Cin", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int),
                 ("Cout", ctypes.c_int), ("KH", ctypes.c_int), ("KW", ctypes.c_int), ("pad", ctypes.c_int),
-                ("stride", ctypes.c_int), ("x_stride", ctypes.c_longlong * 3), ("y_stride", ctypes.c_longlong * 3)]
+                ("stride", ctypes.c_int), ("x_stride", ctypes.c_longlong * 3), ("y_stride", ctypes.c_longlong * 3), ("stride_x", ctypes.c_int)]
 
 
 _vp, _sz, _i, _f = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float

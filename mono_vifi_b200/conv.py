@@ -43,6 +43,9 @@ def _activate(y, act):
 def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, act=None):
     if _backend == "tcgen05" and x.is_cuda:
         from . import conv_tc
+        if groups == 1 and act is None and conv_tc.stem7x7s2_supported(x, weight, stride, padding):
+            stats["tcgen05"] += 1
+            return conv_tc.stem7x7s2(x, weight, bias)
         cin = weight.shape[1]
         if cin % 4 and groups == 1:
             # image-like inputs (3 or 6 channels): zero channels up to a 16-byte pixel; autograd slices the gradient back

@@ -29,8 +29,14 @@ def _timed(tag, flops, fn):
     return r
 
 
+def _pair(v):
+    return (v, v) if isinstance(v, int) else (int(v[0]), int(v[1]))
+
+
 def _desc(B, Cin, H, W, Cout, KH, KW, pad, stride, x, y):
-    d = _lib.Conv2dDesc(B, Cin, H, W, Cout, KH, KW, pad, stride)
+    sy, sx = _pair(stride)
+    d = _lib.Conv2dDesc(B, Cin, H, W, Cout, KH, KW, pad, sy)
+    d.stride_x = sx
     for i, dim in enumerate((0, 2, 3)):  # batch, row, column strides; the channel stride is 1
         d.x_stride[i] = x.stride(dim)
         d.y_stride[i] = y.stride(dim)
@@ -56,7 +62,8 @@ def _as_input(x):
 
 
 def out_hw(H, W, KH, KW, pad, stride):
-    return (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    sy, sx = _pair(stride)
+    return (H + 2 * pad - KH) // sy + 1, (W + 2 * pad - KW) // sx + 1
 
 
 def supported(x, weight, stride, padding, dilation=1, groups=1):
@@ -67,7 +74,7 @@ def supported(x, weight, stride, padding, dilation=1, groups=1):
     sh, sw = pair(stride)
     ph, pw = pair(padding)
     Cout, Cin, KH, KW = weight.shape
-    if sh != sw or sh not in (1, 2) or ph != pw or Cin % 4:
+    if sh not in (1, 2) or sw not in (1, 2) or ph != pw or Cin % 4:
         return False
     return True
 
@@ -134,7 +141,7 @@ class _Conv2dTC(torch.autograd.Function):
             gy = torch.ops.aten.elu_backward(gy, 1.0, 1.0, 1.0, True, ctx.saved_tensors[2])
         gy = _as_input(gy)
         if ctx.needs_input_grad[0]:
-            if stride == 1 and Cout % 4 == 0 and pad <= KH - 1 and pad <= KW - 1:
+            if _pair(stride) == (1, 1) and Cout % 4 == 0 and pad <= KH - 1 and pad <= KW - 1:
                 global _tag
                 launches["dgrad"] += 1
                 _tag = "dgrad"
@@ -155,7 +162,7 @@ def input_grad_library(x, gy, weight, pad, stride):
     """dL/dx of the shapes the tcgen05 dgrad does not cover yet (strided convolutions): cuDNN, counted in conv.stats."""
     from . import conv
     conv.stats["cudnn_dgrad"] = conv.stats.get("cudnn_dgrad", 0) + 1
-    gx, _, _ = torch.ops.aten.convolution_backward(gy, x, weight, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1,
+    gx, _, _ = torch.ops.aten.convolution_backward(gy, x, weight, None, list(_pair(stride)), [pad, pad], [1, 1], False, [0, 0], 1,
                                                    [True, False, False])
     return gx
 
@@ -190,7 +197,7 @@ def weight_grad(x, gy, wshape, pad, stride=1):
     from . import conv
     conv.stats["cudnn_wgrad"] = conv.stats.get("cudnn_wgrad", 0) + 1
     w = torch.empty(wshape, device=x.device, dtype=x.dtype).contiguous(memory_format=torch.channels_last)
-    _, gw, _ = torch.ops.aten.convolution_backward(gy, x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1,
+    _, gw, _ = torch.ops.aten.convolution_backward(gy, x, w, None, list(_pair(stride)), [pad, pad], [1, 1], False, [0, 0], 1,
                                                    [False, True, False])
     return gw
 
@@ -198,5 +205,29 @@ def weight_grad(x, gy, wshape, pad, stride=1):
 def conv2d(x, weight, bias=None, stride=1, padding=0, act=None):
     """act: None | "relu" | "elu" -- applied in the kernel's epilogue (its backward uses the saved output)."""
     pad = padding if isinstance(padding, int) else padding[0]
-    st = stride if isinstance(stride, int) else stride[0]
-    return _Conv2dTC.apply(x, weight, bias, pad, st, ACT[act])
+    st = _pair(stride)
+    return _Conv2dTC.apply(x, weight, bias, pad, st[0] if st[0] == st[1] else st, ACT[act])
+
+
+def stem7x7s2_supported(x, weight, stride, padding):
+    Cout, Cin, KH, KW = weight.shape
+    return (x.is_cuda and (KH, KW) == (7, 7) and _pair(stride) == (2, 2) and _pair(padding) == (3, 3) and Cin <= 8 and
+            x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 and not x.requires_grad)
+
+
+def stem7x7s2(x, weight, bias=None):
+    """The 7x7 stride-2 pad-3 stem on image-like inputs (3 or 6 channels), row-packed: a channels-last pixel has only 4
+    (8) floats, so a filter ROW (7 taps + 1 zero tap = 8 pixels) is ONE contiguous 32- (64-) float K block.  The padded
+    image is viewed as [B, 8*C', H+6, Wo] whose column stride is 2 pixels (overlapping windows -- fine for TMA) and the
+    filter as [Cout, 8*C', 7, 1]: 7 (14) pipeline stages instead of 49, no zero-channel waste, and the weight gradient
+    comes out of the same tcgen05 wgrad kernel (the reshaping of the filter is plain autograd)."""
+    B, Cin, H, W = x.shape
+    Cout = weight.shape[0]
+    Cp = 4 if Cin <= 4 else 8
+    Hp, Wp, Wo = H + 6, W + 8, W // 2
+    xp = torch.zeros(B, Hp, Wp, Cp, device=x.device, dtype=torch.float32)
+    xp[:, 3:3 + H, 3:3 + W, :Cin] = x.permute(0, 2, 3, 1)
+    fake = torch.as_strided(xp, (B, 8 * Cp, Hp, Wo), (Hp * Wp * Cp, 1, Wp * Cp, 2 * Cp))
+    wrow = weight.new_zeros(Cout, 8, Cp, 7)
+    wrow[:, :7, :Cin] = weight.permute(0, 3, 1, 2)          # [co, kw, c, kh]
+    return conv2d(fake, wrow.reshape(Cout, 8 * Cp, 7, 1), bias, stride=(2, 1), padding=0)

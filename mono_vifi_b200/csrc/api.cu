@@ -222,6 +222,7 @@ static mvf::tc::ConvDesc to_desc(const mvf_conv2d_desc* d) {
     mvf::tc::ConvDesc c;
     c.B = d->B; c.Cin = d->Cin; c.H = d->H; c.W = d->W; c.Cout = d->Cout; c.KH = d->KH; c.KW = d->KW; c.pad = d->pad;
     c.stride = d->stride;
+    c.stride_x = d->stride_x > 0 ? d->stride_x : d->stride;
     c.x_sB = d->x_stride[0]; c.x_sH = d->x_stride[1]; c.x_sW = d->x_stride[2];
     c.y_sB = d->y_stride[0]; c.y_sH = d->y_stride[1]; c.y_sW = d->y_stride[2];
     return c;
@@ -263,6 +264,7 @@ static mvf::tc::WgradDesc to_wdesc(const mvf_conv2d_desc* d) {
     mvf::tc::WgradDesc c;
     c.B = d->B; c.Cin = d->Cin; c.H = d->H; c.W = d->W; c.Cout = d->Cout; c.KH = d->KH; c.KW = d->KW; c.pad = d->pad;
     c.stride = d->stride;
+    c.stride_x = d->stride_x > 0 ? d->stride_x : d->stride;
     c.x_sB = d->x_stride[0]; c.x_sH = d->x_stride[1]; c.x_sW = d->x_stride[2];
     c.g_sB = d->y_stride[0]; c.g_sH = d->y_stride[1]; c.g_sW = d->y_stride[2];
     return c;

@@ -46,7 +46,7 @@ struct ConvArgs {
     const float* bias;
     long long y_sB, y_sH, y_sW;  // output strides in elements (channel stride 1)
     int Cout, Ho, Wo;
-    int KH, KW, pad, stride;
+    int KH, KW, pad, stride, stride_x;  // row / column stride of the convolution
     int tw_log2;                 // tile = (1 << tw_log2) x (128 >> tw_log2) output pixels
     int tiles_x, tiles_y;
     int n_cblk;                  // ceil(Cin / 32)
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
                 const int kh = tap / p.KW, kw = tap - kh * p.KW;
                 mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
                 // A: dims (c, x, y, b), box (32, TW, TH, 1) traversed with the conv stride -> smem [pixel][32 c]
-                tma_load_4d(smA + s * A_STAGE_BYTES, &mapA, &full_bar[s], cb * BLOCK_K, x0 * p.stride + kw - p.pad,
+                tma_load_4d(smA + s * A_STAGE_BYTES, &mapA, &full_bar[s], cb * BLOCK_K, x0 * p.stride_x + kw - p.pad,
                             y0 * p.stride + kh - p.pad, b);
                 // B: dims (k within block, cout, tap * n_cblk + cb), box (32, N_TILE, 1) -> smem [cout][32 k]
                 tma_load_3d(smB + s * C::B_STAGE_BYTES, &mapB, &full_bar[s], 0, n0, it);
@@ -534,7 +534,7 @@ static int out_size(int n, int k, int pad, int stride) { return (n + 2 * pad - k
 
 const char* conv_check(const ConvDesc& d) {
     if (d.B <= 0 || d.Cin <= 0 || d.H <= 0 || d.W <= 0 || d.Cout <= 0 || d.KH <= 0 || d.KW <= 0) return "non-positive size";
-    if (d.stride != 1 && d.stride != 2) return "stride must be 1 or 2";
+    if ((d.stride != 1 && d.stride != 2) || (d.stride_x != 1 && d.stride_x != 2)) return "strides must be 1 or 2";
     if (d.Cin % 4 != 0) return "input channels must be a multiple of 4 (TMA: 16-byte rows)";
     if ((d.x_sH % 4) || (d.x_sW % 4) || (d.x_sB % 4)) return "input strides must be multiples of 4 elements (TMA: 16 bytes)";
     if (d.pad < 0) return "negative padding";
@@ -668,15 +668,15 @@ cudaError_t conv_forward(const ConvDesc& d, const float* x, const float* w_packe
         *why = "input / packed filter pointers must be 16-byte aligned";
         return cudaErrorInvalidValue;
     }
-    const int Ho = out_size(d.H, d.KH, d.pad, d.stride), Wo = out_size(d.W, d.KW, d.pad, d.stride);
-    if (d.stride == 1 && d.KH * d.KW > 1 && d.KW <= 16 && !getenv("MVF_CONV_NO_PATCH"))
+    const int Ho = out_size(d.H, d.KH, d.pad, d.stride), Wo = out_size(d.W, d.KW, d.pad, d.stride_x);
+    if (d.stride == 1 && d.stride_x == 1 && d.KH * d.KW > 1 && d.KW <= 16 && !getenv("MVF_CONV_NO_PATCH"))
         return conv_forward_patch(d, x, w_packed, bias, y, act, st, why, enc, Ho, Wo);
     ConvArgs a;
     a.y = y;
     a.bias = bias;
     a.y_sB = d.y_sB; a.y_sH = d.y_sH; a.y_sW = d.y_sW;
     a.Cout = d.Cout; a.Ho = Ho; a.Wo = Wo;
-    a.KH = d.KH; a.KW = d.KW; a.pad = d.pad; a.stride = d.stride;
+    a.KH = d.KH; a.KW = d.KW; a.pad = d.pad; a.stride = d.stride; a.stride_x = d.stride_x;
     // tile shape: the (2^j x 128/2^j) patch that covers the output with the least padding (ties: the widest)
     int best = 5;
     long long best_cost = -1;
@@ -702,8 +702,8 @@ cudaError_t conv_forward(const ConvDesc& d, const float* x, const float* w_packe
     {   // input as (c, x, y, b); strides in bytes for dims 1..3; the box walks x and y with the convolution stride
         cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
         cuuint64_t strides[3] = {(cuuint64_t)d.x_sW * 4, (cuuint64_t)d.x_sH * 4, (cuuint64_t)d.x_sB * 4};
-        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)(TW * d.stride), (cuuint32_t)(TH * d.stride), 1};
-        cuuint32_t es[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
+        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)(TW * d.stride_x), (cuuint32_t)(TH * d.stride), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)d.stride_x, (cuuint32_t)d.stride, 1};
         CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -10,7 +10,7 @@ namespace tc {
 // output y[b][oy][ox][co] with strides (y_sB, y_sH, y_sW, 1), Ho = (H + 2 pad - KH) / stride + 1.
 struct ConvDesc {
     int B, Cin, H, W;
-    int Cout, KH, KW, pad, stride;
+    int Cout, KH, KW, pad, stride, stride_x;  // stride: rows, stride_x: columns
     long long x_sB, x_sH, x_sW;
     long long y_sB, y_sH, y_sW;
 };
@@ -18,7 +18,7 @@ struct ConvDesc {
 // wgrad problem on channels-last tensors: dw[Cout,Cin,KH,KW] = sum_pixels gy . x  (conv_wgrad.cu)
 struct WgradDesc {
     int B, Cin, H, W;
-    int Cout, KH, KW, pad, stride;
+    int Cout, KH, KW, pad, stride, stride_x;
     long long x_sB, x_sH, x_sW;
     long long g_sB, g_sH, g_sW;
 };

@@ -29,7 +29,7 @@ constexpr int NTHREADS = 192;
 
 struct WgradArgs {
     float* partial;  // [ksplit][taps][Cout_pad128][Cin_pad32]
-    int Cout, Cin, KH, KW, pad, stride;
+    int Cout, Cin, KH, KW, pad, stride, stride_x;
     int Ho, Wo, B;
     int pw, ph;      // pixel patch of one pipeline stage: pw x ph output pixels (pw * ph a multiple of 8, <= 64)
     int patches_x, patches_y;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
                     // one box per tap, walked with the convolution stride -> smem [tap][pixel][32 ci]
                     int kh = 0, kw = 0;
                     for (int t = 0; t < taps; ++t) {
-                        tma_load_4d(st + p.a_bytes + t * (kp * 128), &mapX, &full_bar[s], ci0, ox0 * p.stride + kw - p.pad,
+                        tma_load_4d(st + p.a_bytes + t * (kp * 128), &mapX, &full_bar[s], ci0, ox0 * p.stride_x + kw - p.pad,
                                     oy0 * p.stride + kh - p.pad, b);
                         if (++kw == p.KW) { kw = 0; ++kh; }
                     }
@@ -226,9 +226,9 @@ struct Plan {
 Plan make_plan(const WgradDesc& d) {
     Plan pl;
     pl.Ho = out_size(d.H, d.KH, d.pad, d.stride);
-    pl.Wo = out_size(d.W, d.KW, d.pad, d.stride);
+    pl.Wo = out_size(d.W, d.KW, d.pad, d.stride_x);
     const int taps = d.KH * d.KW;
-    pl.shared_patch = (d.stride == 1 && taps > 1 && !getenv("MVF_WGRAD_NO_PATCH")) ? 1 : 0;
+    pl.shared_patch = (d.stride == 1 && d.stride_x == 1 && taps > 1 && !getenv("MVF_WGRAD_NO_PATCH")) ? 1 : 0;
     if (pl.shared_patch) {
         // one output-row segment of pw pixels per stage (pw a multiple of 8, <= 64): least padding, then the widest
         int best = 32;
@@ -285,7 +285,7 @@ Plan make_plan(const WgradDesc& d) {
 
 const char* wgrad_check(const WgradDesc& d) {
     if (d.B <= 0 || d.Cin <= 0 || d.H <= 0 || d.W <= 0 || d.Cout <= 0 || d.KH <= 0 || d.KW <= 0) return "non-positive size";
-    if (d.stride != 1 && d.stride != 2) return "stride must be 1 or 2";
+    if ((d.stride != 1 && d.stride != 2) || (d.stride_x != 1 && d.stride_x != 2)) return "strides must be 1 or 2";
     if (d.KH * d.KW > MAX_TAPS) return "more than 9 filter taps";
     if (d.Cin % 4 != 0 || d.Cout % 4 != 0) return "channel counts must be multiples of 4 (TMA: 16-byte pixels)";
     if (d.Cout > 32 && d.Cout % 32 != 0) return "Cout above 32 must be a multiple of 32";
@@ -316,7 +316,7 @@ cudaError_t conv_wgrad(const WgradDesc& d, const float* x, const float* gy, floa
     const int PW = pl.pw, PH = pl.ph;
     WgradArgs a;
     a.partial = workspace;
-    a.Cout = d.Cout; a.Cin = d.Cin; a.KH = d.KH; a.KW = d.KW; a.pad = d.pad; a.stride = d.stride;
+    a.Cout = d.Cout; a.Cin = d.Cin; a.KH = d.KH; a.KW = d.KW; a.pad = d.pad; a.stride = d.stride; a.stride_x = d.stride_x;
     a.Ho = pl.Ho; a.Wo = pl.Wo; a.B = d.B;
     a.pw = pl.pw; a.ph = pl.ph; a.patches_x = pl.patches_x; a.patches_y = pl.patches_y; a.n_patches = pl.n_patches;
     a.stages = pl.stages;
@@ -340,8 +340,8 @@ cudaError_t conv_wgrad(const WgradDesc& d, const float* x, const float* gy, floa
     {   // x as (ci, ix, iy, b), walked with the convolution stride
         cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
         cuuint64_t strides[3] = {(cuuint64_t)d.x_sW * 4, (cuuint64_t)d.x_sH * 4, (cuuint64_t)d.x_sB * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)(PW * d.stride), (cuuint32_t)(PH * d.stride), 1};
-        cuuint32_t es[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
+        cuuint32_t box[4] = {32, (cuuint32_t)(PW * d.stride_x), (cuuint32_t)(PH * d.stride), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)d.stride_x, (cuuint32_t)d.stride, 1};
         if (pl.shared_patch) {
             box[1] = (cuuint32_t)pl.pwx;
             box[2] = (cuuint32_t)d.KH;

@@ -168,3 +168,25 @@ def test_wgrad_vs_fp64(case):
     # bitwise reproducible (fixed-order split-K reduction)
     gw2 = conv_tc.weight_grad(conv_tc._as_input(x), gy, (Cout, Cin, k, k), pad, stride)
     assert torch.equal(gw, gw2)
+
+
+@pytest.mark.parametrize("cin", [3, 6])
+def test_row_packed_stem_matches_fp64(cin):
+    """7x7 stride-2 pad-3 stem on 3- / 6-channel images through the row-packed path (fprop + wgrad on tcgen05)"""
+    import torch
+    from mono_vifi_b200 import conv, conv_tc
+    conv.set_backend("tcgen05")
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn(2, cin, 64, 96, device="cuda", generator=g)
+    w = (torch.randn(64, cin, 7, 7, device="cuda", generator=g) / (cin * 49) ** 0.5).requires_grad_(True)
+    before = dict(conv_tc.launches)
+    y = conv.conv2d(x, w, None, 2, 3)
+    gy = torch.randn(y.shape, device="cuda", generator=g)
+    y.backward(gy)
+    assert conv_tc.launches["fprop"] == before["fprop"] + 1 and conv_tc.launches["wgrad"] == before["wgrad"] + 1
+    wr = w.detach().double().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(x.double(), wr, None, 2, 3)
+    yr.backward(gy.double())
+    assert y.shape == yr.shape
+    assert (y.double() - yr).abs().max().item() <= 2e-3 * yr.abs().max().item()
+    assert (w.grad.double() - wr.grad).abs().max().item() <= 3e-3 * wr.grad.abs().max().item()
