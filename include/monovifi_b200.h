@@ -166,6 +166,12 @@ int mvf_upcat_pad_fwd(const float* a, const float* skip, float* y, int B, int Ca
 int mvf_upcat_pad_bwd(const float* grad_y, float* grad_a, float* grad_skip, int B, int Ca, int Cs, int H, int W, int upsample,
                       void* stream);
 
+/* MaxPool2d(kernel 3, stride 2, padding 1) of the ResNet stems (torchvision ResNet.maxpool, used by monodepth2.py:39 and
+ * posenet.py:91) on dense channels-last tensors; idx[B,Ho,Wo,C] (uint8) holds the in-window position of each maximum and
+ * feeds the gather-form (atomic-free, deterministic) backward.  C % 4 == 0; Ho = (H-1)/2+1. */
+int mvf_maxpool3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int C, int H, int W, void* stream);
+int mvf_maxpool3s2_bwd(const float* grad_y, const unsigned char* idx, float* grad_x, int B, int C, int H, int W, void* stream);
+
 /* device self-test: q_sequence[i] = the kernels' shared-reciprocal division of a[i] by b[i], q_ieee[i] = the
  * IEEE quotient (div.rn.f32); the two must be bit-identical for operands in the normal range. */
 int mvf_selftest_division(const float* a, const float* b, float* q_sequence, float* q_ieee, size_t n, void* stream);

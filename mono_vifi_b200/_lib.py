@@ -54,6 +54,8 @@ SIGNATURES = {
     "mvf_conv2d_wgrad": (_i, [_CD, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mvf_upcat_pad_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mvf_upcat_pad_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "mvf_maxpool3s2_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "mvf_maxpool3s2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mvf_selftest_umma": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "mvf_selftest_umma_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mvf_conv2d_debug_buffer": (None, [_vp]),

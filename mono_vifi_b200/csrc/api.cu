@@ -308,4 +308,14 @@ int mvf_upcat_pad_bwd(const float* grad_y, float* grad_a, float* grad_skip, int 
     MVF_RUN("mvf_upcat_pad_bwd", mvf::upcat_pad_bwd(grad_y, grad_a, grad_skip, B, Ca, Cs, H, W, upsample, (cudaStream_t)stream));
 }
 
+/* ---- MaxPool2d(3, 2, 1), channels-last ------------------------------------------------------------------------ */
+int mvf_maxpool3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int C, int H, int W, void* stream) {
+    if (!x || !y || !idx || B <= 0 || C <= 0 || (C % 4) || H < 2 || W < 2) return fail(MVF_ERR_INVALID, "mvf_maxpool3s2_fwd: bad argument (C % 4 == 0)");
+    MVF_RUN("mvf_maxpool3s2_fwd", mvf::maxpool3s2_fwd(x, y, idx, B, C, H, W, (cudaStream_t)stream));
+}
+int mvf_maxpool3s2_bwd(const float* grad_y, const unsigned char* idx, float* grad_x, int B, int C, int H, int W, void* stream) {
+    if (!grad_y || !idx || !grad_x || B <= 0 || C <= 0 || (C % 4) || H < 2 || W < 2) return fail(MVF_ERR_INVALID, "mvf_maxpool3s2_bwd: bad argument (C % 4 == 0)");
+    MVF_RUN("mvf_maxpool3s2_bwd", mvf::maxpool3s2_bwd(grad_y, idx, grad_x, B, C, H, W, (cudaStream_t)stream));
+}
+
 }  // extern "C"

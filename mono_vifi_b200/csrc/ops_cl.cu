@@ -94,12 +94,12 @@ __global__ void upcat_pad_bwd_skip_kernel(const float4* __restrict__ gy, float4*
     }
 }
 
-int grid_for(long long total) {
+}  // namespace
+
+static int grid_for(long long total) {
     long long b = (total + 255) / 256;
     return (int)(b < 148 * 16 ? (b < 1 ? 1 : b) : 148 * 16);
 }
-
-}  // namespace
 
 cudaError_t upcat_pad_fwd(const float* a, const float* skip, float* y, int B, int Ca, int Cs, int H, int W, int up, cudaStream_t st) {
     const long long total = (long long)B * (H + 2) * (W + 2) * ((Ca + Cs) / 4);
@@ -116,6 +116,96 @@ cudaError_t upcat_pad_bwd(const float* gy, float* ga, float* gskip, int B, int C
         const long long total = (long long)B * H * W * (Cs / 4);
         upcat_pad_bwd_skip_kernel<<<grid_for(total), 256, 0, st>>>((const float4*)gy, (float4*)gskip, B, Ca / 4, Cs / 4, H, W);
     }
+    return cudaGetLastError();
+}
+
+}  // namespace mvf
+
+// ---- MaxPool2d(kernel 3, stride 2, padding 1), channels-last (torchvision ResNet stem: monodepth2.py:39, posenet.py:91) ----
+// forward writes the pooled value and the position of the maximum inside the 3x3 window (0..8, first maximum wins, as
+// ATen does); backward is a gather: every input pixel collects the gradient of the (at most four) windows whose maximum
+// it is, so no atomics and a deterministic result.
+namespace mvf {
+namespace {
+
+__global__ void maxpool3s2_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, uchar4* __restrict__ idx, int B, int C4,
+                                      int H, int W, int Ho, int Wo) {
+    const long long total = (long long)B * Ho * Wo * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        long long r = i / C4;
+        const int ox = (int)(r % Wo);
+        r /= Wo;
+        const int oy = (int)(r % Ho), b = (int)(r / Ho);
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        uchar4 k = make_uchar4(0, 0, 0, 0);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int iy = 2 * oy - 1 + dy;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ix = 2 * ox - 1 + dx;
+                if (ix < 0 || ix >= W) continue;
+                const float4 v = __ldg(x + (((long long)b * H + iy) * W + ix) * C4 + c);
+                const unsigned char t = (unsigned char)(dy * 3 + dx);
+                if (v.x > m.x || v.x != v.x) { m.x = v.x; k.x = t; }
+                if (v.y > m.y || v.y != v.y) { m.y = v.y; k.y = t; }
+                if (v.z > m.z || v.z != v.z) { m.z = v.z; k.z = t; }
+                if (v.w > m.w || v.w != v.w) { m.w = v.w; k.w = t; }
+            }
+        }
+        y[i] = m;
+        idx[i] = k;
+    }
+}
+
+__global__ void maxpool3s2_bwd_kernel(const float4* __restrict__ gy, const uchar4* __restrict__ idx, float4* __restrict__ gx, int B,
+                                      int C4, int H, int W, int Ho, int Wo) {
+    const long long total = (long long)B * H * W * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        long long r = i / C4;
+        const int ix = (int)(r % W);
+        r /= W;
+        const int iy = (int)(r % H), b = (int)(r / H);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // windows (oy, ox) with 2*oy - 1 + dy == iy, dy in 0..2
+        for (int oy = (iy + 1) / 2 - ((iy & 1) ? 1 : 0); oy <= (iy + 1) / 2; ++oy) {
+            if (oy < 0 || oy >= Ho) continue;
+            const int dy = iy - (2 * oy - 1);
+            if (dy < 0 || dy > 2) continue;
+            for (int ox = (ix + 1) / 2 - ((ix & 1) ? 1 : 0); ox <= (ix + 1) / 2; ++ox) {
+                if (ox < 0 || ox >= Wo) continue;
+                const int dx = ix - (2 * ox - 1);
+                if (dx < 0 || dx > 2) continue;
+                const long long o = (((long long)b * Ho + oy) * Wo + ox) * C4 + c;
+                const uchar4 k = __ldg(idx + o);
+                const float4 g = __ldg(gy + o);
+                const unsigned char t = (unsigned char)(dy * 3 + dx);
+                if (k.x == t) acc.x += g.x;
+                if (k.y == t) acc.y += g.y;
+                if (k.z == t) acc.z += g.z;
+                if (k.w == t) acc.w += g.w;
+            }
+        }
+        gx[i] = acc;
+    }
+}
+
+}  // namespace
+
+cudaError_t maxpool3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int C, int H, int W, cudaStream_t st) {
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const long long total = (long long)B * Ho * Wo * (C / 4);
+    maxpool3s2_fwd_kernel<<<grid_for(total), 256, 0, st>>>((const float4*)x, (float4*)y, (uchar4*)idx, B, C / 4, H, W, Ho, Wo);
+    return cudaGetLastError();
+}
+
+cudaError_t maxpool3s2_bwd(const float* gy, const unsigned char* idx, float* gx, int B, int C, int H, int W, cudaStream_t st) {
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const long long total = (long long)B * H * W * (C / 4);
+    maxpool3s2_bwd_kernel<<<grid_for(total), 256, 0, st>>>((const float4*)gy, (const uchar4*)idx, (float4*)gx, B, C / 4, H, W, Ho, Wo);
     return cudaGetLastError();
 }
 

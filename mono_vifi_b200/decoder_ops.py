@@ -66,3 +66,42 @@ class _UpcatPad(torch.autograd.Function):
 def upcat_pad(a, skip=None, upsample=False):
     """ReflectionPad2d(1)(cat([upsample(a) if upsample else a, skip], 1)) -> [B, Ca+Cs, H+2, W+2], channels-last."""
     return _UpcatPad.apply(a, skip, bool(upsample))
+
+
+class _MaxPool3s2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _dense_cl(x)
+        B, C, H, W = x.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty(B, Ho, Wo, C, device=x.device, dtype=torch.float32).permute(0, 3, 1, 2)
+        idx = torch.empty(B, Ho, Wo, C, device=x.device, dtype=torch.uint8)
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(_lib.lib().mvf_maxpool3s2_fwd(x.data_ptr(), y.data_ptr(), idx.data_ptr(), B, C, H, W, st), "mvf_maxpool3s2_fwd")
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (idx,) = ctx.saved_tensors
+        B, C, H, W = ctx.dims
+        gy = _dense_cl(gy)
+        gx = torch.empty(B, H, W, C, device=gy.device, dtype=torch.float32).permute(0, 3, 1, 2)
+        st = torch.cuda.current_stream(gy.device).cuda_stream
+        _lib.check(_lib.lib().mvf_maxpool3s2_bwd(gy.data_ptr(), idx.data_ptr(), gx.data_ptr(), B, C, H, W, st), "mvf_maxpool3s2_bwd")
+        return gx
+
+
+def maxpool3s2(x):
+    """nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on a channels-last CUDA tensor (C % 4 == 0)."""
+    return _MaxPool3s2.apply(x)
+
+
+class MaxPool3s2(torch.nn.Module):
+    """parameter-free drop-in for torchvision ResNet's `maxpool` (same position in the module tree, no state_dict keys)"""
+
+    def forward(self, x):
+        if x.is_cuda and x.dim() == 4 and x.shape[1] % 4 == 0:
+            return maxpool3s2(x)
+        return torch.nn.functional.max_pool2d(x, 3, 2, 1)

@@ -5,6 +5,7 @@ Reference: monodepth2.py:16-31, posenet.py:10-52 (both wrap torchvision.models.r
 import torch.nn as nn
 
 from ..conv import Conv2d
+from ..decoder_ops import MaxPool3s2
 
 
 class BasicBlock(nn.Module):
@@ -70,7 +71,7 @@ class ResNet(nn.Module):
         self.conv1 = Conv2d(in_channels, 64, kernel_size=7, stride=2, padding=3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         self.relu = nn.ReLU(inplace=True)
-        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        self.maxpool = MaxPool3s2()  # MaxPool2d(3, 2, 1): own channels-last kernels on CUDA, F.max_pool2d elsewhere
         self.layer1 = self._make_layer(block, 64, layers[0])
         self.layer2 = self._make_layer(block, 128, layers[1], stride=2)
         self.layer3 = self._make_layer(block, 256, layers[2], stride=2)

@@ -52,3 +52,21 @@ def test_convblock_fast_path_matches_reference_sequence():
     ref.backward(gy.double())
     for got, want in ((x.grad, xr.grad), (skip.grad, sr.grad), (blk.conv.conv.weight.grad, w.grad), (blk.conv.conv.bias.grad, b.grad)):
         assert (got.double() - want).abs().max().item() <= 4e-3 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 6, 10), (1, 64, 32, 48), (3, 4, 7, 9), (2, 64, 96, 320)])
+def test_maxpool3s2_matches_torch(shape):
+    import torch
+    import torch.nn.functional as F
+    from mono_vifi_b200 import decoder_ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    # quantised values: plenty of ties inside windows, so the first-maximum rule is exercised
+    x = (torch.randint(0, 6, shape, device="cuda", generator=g).float() / 4).requires_grad_(True)
+    y = decoder_ops.maxpool3s2(x)
+    xr = x.detach().clone().requires_grad_(True)
+    ref = F.max_pool2d(xr, 3, 2, 1)
+    assert torch.equal(y, ref)
+    gy = torch.randn(ref.shape, device="cuda", generator=g)
+    y.backward(gy)
+    ref.backward(gy)
+    assert torch.allclose(x.grad, xr.grad, rtol=1e-6, atol=1e-6)
