@@ -175,12 +175,16 @@ def weight_grad(x, gy, wshape, pad, stride=1):
     are counted in conv.stats -- never silently."""
     Cout, Cin, KH, KW = wshape
     B, _, H, W = x.shape
+    if Cout % 4:
+        # e.g. the 1-channel disparity head: zero channels up to a 16-byte pixel, slice the result back
+        extra = 4 - Cout % 4
+        gyp = torch.zeros(B, gy.shape[2], gy.shape[3], Cout + extra, device=gy.device, dtype=torch.float32).permute(0, 3, 1, 2)
+        gyp[:, :Cout] = gy
+        return weight_grad(x, gyp, (Cout + extra, Cin, KH, KW), pad, stride)[:Cout]
     gy = _as_input(gy)
-    if Cout == 1 and gy.stride(3) != 1:
-        gy = gy.contiguous()
     d = _desc(B, Cin, H, W, Cout, KH, KW, pad, stride, x, gy)
     L = _lib.lib()
-    if Cout % 4 == 0 and L.mvf_conv2d_wgrad_supported(d):
+    if L.mvf_conv2d_wgrad_supported(d):
         n = L.mvf_conv2d_wgrad_workspace_floats(d)
         key = (x.device.index, _stream(x))
         ws = _wgrad_ws.get(key)
