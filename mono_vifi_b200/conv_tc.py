@@ -141,12 +141,18 @@ class _Conv2dTC(torch.autograd.Function):
             gy = torch.ops.aten.elu_backward(gy, 1.0, 1.0, 1.0, True, ctx.saved_tensors[2])
         gy = _as_input(gy)
         if ctx.needs_input_grad[0]:
-            if _pair(stride) == (1, 1) and Cout % 4 == 0 and pad <= KH - 1 and pad <= KW - 1:
+            if _pair(stride) == (1, 1) and pad <= KH - 1 and pad <= KW - 1:
+                gyd, wd = gy, weight
+                if Cout % 4:  # e.g. the 1-channel disparity head: zero channels up to a 16-byte pixel
+                    extra = 4 - Cout % 4
+                    gyd = torch.zeros(gy.shape[0], gy.shape[2], gy.shape[3], Cout + extra, device=gy.device).permute(0, 3, 1, 2)
+                    gyd[:, :Cout] = gy
+                    wd = torch.nn.functional.pad(weight, (0, 0, 0, 0, 0, 0, 0, extra))
                 global _tag
                 launches["dgrad"] += 1
                 _tag = "dgrad"
                 try:
-                    gx = conv_forward_raw(gy, pack_filters(weight, dgrad=True), None, Cin, KH, KW, KH - 1 - pad)
+                    gx = conv_forward_raw(gyd, pack_filters(wd, dgrad=True), None, Cin, KH, KW, KH - 1 - pad)
                 finally:
                     _tag = "fprop"
             else:

@@ -210,6 +210,7 @@ struct PatchArgs {
     int n_cblk, act;
     int patch_bytes, patch_stride;  // bytes landed per patch, distance between the two patch buffers (1024-aligned)
     int n_mtiles, n_tiles;       // M tiles (B * nseg * tiles_y), all tiles (M tiles x N tiles)
+    int b_resident;              // 1: the whole filter bank of the CTA's couts fits in the ring and is loaded ONCE per CTA
     int tma_store;               // 1: epilogue stages slabs in shared memory and stores them with TMA; 0: per-thread stores
     int dbg;                     // timing experiments only: 4 = no MMAs, 8 = no TMA loads
 };
@@ -271,6 +272,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
         if (lane == 0) {
             int bs = 0, bph = 0;  // filter ring slot / phase
             int ab = 0, aph = 0;  // patch buffer / phase
+            if (p.b_resident) {
+                // small layers: all (tap, channel-block) filter tiles stay in shared memory for the CTA's lifetime
+                const int nb_tiles = taps * p.n_cblk;
+                mbar_arrive_expect_tx(&b_full[0], nb_tiles * B_STAGE_BYTES);
+                for (int i = 0; i < nb_tiles; ++i) tma_load_3d(smB + i * B_STAGE_BYTES, &mapB, &b_full[0], 0, 0, i);
+            }
             for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
                 const int m = t % p.n_mtiles, nt = t / p.n_mtiles;
                 const int seg = m % p.nseg, ty = (m / p.nseg) % p.tiles_y, b = m / (p.nseg * p.tiles_y);
@@ -285,6 +292,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
                         tma_load_4d(smA + ab * p.patch_stride, &mapA, &a_full[ab], cb * BLOCK_K, xs - p.pad, ys - p.pad, b);
                     }
                     if (++ab == 2) { ab = 0; aph ^= 1; }
+                    if (p.b_resident) continue;
                     int kb = cb;  // filter tile index = tap * n_cblk + cb
                     for (int tp = 0; tp < taps; ++tp, kb += p.n_cblk) {
                         mbar_wait(&b_empty[bs], bph ^ 1);
@@ -305,6 +313,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
         const uint64_t desc_hi = make_smem_desc(0, 16, 1024, SWZ_128B);  // everything but the start address
         const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
         int bs = 0, bph = 0, ab = 0, aph = 0, acc = 0, accph = 0;
+        if (p.b_resident) mbar_wait(&b_full[0], 0);
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
             mbar_wait(&acc_empty[acc], accph ^ 1);  // the epilogue has drained this accumulator buffer
             tc_fence_after();
@@ -314,9 +323,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
                 const uint32_t a_base = smA_u + (uint32_t)(ab * p.patch_stride);
                 int kh = 0, kw = 0;
                 for (int tp = 0; tp < taps; ++tp) {
-                    mbar_wait(&b_full[bs], bph);
+                    if (!p.b_resident) mbar_wait(&b_full[bs], bph);
                     tc_fence_after();
-                    const uint32_t b_lo = (smB_u + (uint32_t)(bs * B_STAGE_BYTES)) >> 4;
+                    const uint32_t b_lo = (smB_u + (uint32_t)((p.b_resident ? tp * p.n_cblk + cb : bs) * B_STAGE_BYTES)) >> 4;
                     if (elect_one()) {
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) {
@@ -327,7 +336,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
                                 umma_tf32(d_base + (uint32_t)(mt * N_TILE), desc_hi | (uint64_t)(a_lo + 2 * kg),
                                           desc_hi | (uint64_t)(b_lo + 2 * kg), idesc, (cb > 0 || tp > 0 || kg > 0) ? 1u : 0u);
                         }
-                        umma_commit(&b_empty[bs]);
+                        if (!p.b_resident) umma_commit(&b_empty[bs]);
                     }
                     __syncwarp();
                     if (++bs == NB) { bs = 0; bph ^= 1; }
@@ -496,7 +505,7 @@ cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const ConvA
 template <int N_TILE, int MT>
 cudaError_t launch_patch(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapY, const PatchArgs& a,
                          cudaStream_t st) {
-    constexpr int NB = (N_TILE >= 128) ? 4 : 8;  // 64 KB / 64 KB / 32 KB / 16 KB of filter tiles in flight
+    constexpr int NB = (N_TILE >= 128) ? 4 : (N_TILE >= 64 ? 8 : 16);  // 64 / 64 / 64 / 32 KB of filter tiles
     const int smem = NB * N_TILE * BLOCK_K * 4 + 2 * TILE_M * (N_TILE < 32 ? N_TILE : 32) * 4 + 2 * a.patch_stride + 1024 + 256;
     static int attr_max = 0;
     if (smem > attr_max) {
@@ -592,7 +601,9 @@ static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const f
     a.n_mtiles = d.B * a.nseg * a.tiles_y;
     a.n_tiles = a.n_mtiles * n_ntiles;
     const int slab = n_tile < 32 ? n_tile : 32;
-    if ((n_tile >= 128 ? 4 : 8) * n_tile * BLOCK_K * 4 + 2 * TILE_M * slab * 4 + 2 * a.patch_stride + 1280 > 227 * 1024) {
+    const int nb_ring = n_tile >= 128 ? 4 : (n_tile >= 64 ? 8 : 16);
+    a.b_resident = (n_ntiles == 1 && d.KH * d.KW * a.n_cblk <= nb_ring && !getenv("MVF_CONV_NO_RESIDENT")) ? 1 : 0;
+    if (nb_ring * n_tile * BLOCK_K * 4 + 2 * TILE_M * slab * 4 + 2 * a.patch_stride + 1280 > 227 * 1024) {
         *why = "patch does not fit in shared memory";
         return cudaErrorInvalidValue;
     }

@@ -200,6 +200,44 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     }
 }
 
+// same reduction for many splits and few outputs (high-resolution, narrow layers): one WARP per group of 4 cins; lane l
+// adds splits l, l+32, ... and a fixed shuffle tree combines the lanes -- still one summation order, so deterministic
+__global__ void wgrad_reduce_warp_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin, int taps,
+                                         int ksplit, int cout_pad, int cin_pad) {
+    const int cin4 = (Cin + 3) / 4;
+    const long long total = (long long)Cout * taps * cin4;
+    const size_t split_stride = (size_t)taps * cout_pad * cin_pad;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp0; i < total; i += nwarps) {
+        const int c4 = (int)(i % cin4);
+        long long r = i / cin4;
+        const int t = (int)(r % taps);
+        const int co = (int)(r / taps);
+        const float* src = partial + ((size_t)t * cout_pad + co) * cin_pad + 4 * c4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = lane; s < ksplit; s += 32) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + s * split_stride));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+            acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+        }
+        if (lane == 0) {
+            const int ci = 4 * c4;
+            float* o = dw + ((long long)co * Cin + ci) * taps + t;
+            o[0] = acc.x;
+            if (ci + 1 < Cin) o[taps] = acc.y;
+            if (ci + 2 < Cin) o[2 * taps] = acc.z;
+            if (ci + 3 < Cin) o[3 * taps] = acc.w;
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -368,8 +406,14 @@ cudaError_t conv_wgrad(const WgradDesc& d, const float* x, const float* gy, floa
     if (e != cudaSuccess) return e;
     const long long total = (long long)d.Cout * taps * ((d.Cin + 3) / 4);
     const int threads = 256;
-    const int blocks = (int)((total + threads - 1) / threads < 1184 ? (total + threads - 1) / threads : 1184);
-    wgrad_reduce_kernel<<<blocks, threads, 0, st>>>(workspace, dw, d.Cout, d.Cin, taps, pl.ksplit, pl.cout_pad, pl.cin_pad);
+    if (pl.ksplit >= 16) {
+        const long long nb = (total + 7) / 8;  // 8 warps per block, one warp per output group
+        wgrad_reduce_warp_kernel<<<(int)(nb < 148 * 8 ? nb : 148 * 8), threads, 0, st>>>(workspace, dw, d.Cout, d.Cin, taps, pl.ksplit,
+                                                                                        pl.cout_pad, pl.cin_pad);
+    } else {
+        const int blocks = (int)((total + threads - 1) / threads < 1184 ? (total + threads - 1) / threads : 1184);
+        wgrad_reduce_kernel<<<blocks, threads, 0, st>>>(workspace, dw, d.Cout, d.Cin, taps, pl.ksplit, pl.cout_pad, pl.cin_pad);
+    }
     return cudaGetLastError();
 }
 
