@@ -172,6 +172,21 @@ int mvf_upcat_pad_bwd(const float* grad_y, float* grad_a, float* grad_skip, int 
 int mvf_maxpool3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int C, int H, int W, void* stream);
 int mvf_maxpool3s2_bwd(const float* grad_y, const unsigned char* idx, float* grad_x, int B, int C, int H, int W, void* stream);
 
+/* ---- fused training-mode BatchNorm2d (+ residual add) + ReLU on dense channels-last tensors [P pixels][C] -----------
+ * The bn -> (+= identity) -> relu tail of torchvision's BasicBlock / Bottleneck (networks/monodepth2.py:16-31,
+ * networks/posenet.py:10-52, hrnet_encoder.py:58-139).  fwd: batch statistics (biased variance for the normalisation),
+ * running statistics updated as nn.BatchNorm2d does (momentum, unbiased variance; pass NULL to skip), save_mean /
+ * save_invstd [C] kept for the backward.  bwd: grad_x, grad_gamma, grad_beta and (optional) grad_identity = masked grad_y.
+ * identity / y may be NULL (no residual / relu = 0).  workspace: mvf_bn_workspace_floats(P, C) floats of scratch; the
+ * per-CTA partial sums are added in a fixed order (bitwise reproducible).  C % 4 == 0, C <= 1024. */
+size_t mvf_bn_workspace_floats(long long P, int C);
+int mvf_bn_relu_fwd(const float* x, const float* identity, float* y, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float* save_mean, float* save_invstd, float* workspace, size_t workspace_floats, long long P,
+                    int C, float eps, float momentum, int relu, void* stream);
+int mvf_bn_relu_bwd(const float* x, const float* grad_y, const float* y, const float* gamma, const float* save_mean,
+                    const float* save_invstd, float* grad_x, float* grad_identity, float* grad_gamma, float* grad_beta,
+                    float* workspace, size_t workspace_floats, long long P, int C, int relu, void* stream);
+
 /* device self-test: q_sequence[i] = the kernels' shared-reciprocal division of a[i] by b[i], q_ieee[i] = the
  * IEEE quotient (div.rn.f32); the two must be bit-identical for operands in the normal range. */
 int mvf_selftest_division(const float* a, const float* b, float* q_sequence, float* q_ieee, size_t n, void* stream);

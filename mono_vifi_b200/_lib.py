@@ -56,6 +56,9 @@ SIGNATURES = {
     "mvf_upcat_pad_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mvf_maxpool3s2_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mvf_maxpool3s2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "mvf_bn_workspace_floats": (_sz, [ctypes.c_longlong, _i]),
+    "mvf_bn_relu_fwd": (_i, [_vp] * 10 + [_sz, ctypes.c_longlong, _i, _f, _f, _i, _vp]),
+    "mvf_bn_relu_bwd": (_i, [_vp] * 11 + [_sz, ctypes.c_longlong, _i, _i, _vp]),
     "mvf_selftest_umma": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "mvf_selftest_umma_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mvf_conv2d_debug_buffer": (None, [_vp]),

@@ -1,0 +1,97 @@
+"""Training-mode BatchNorm2d fused with the residual add and ReLU that follow it in the ResNet / HRNet blocks
+(C ABI: mvf_bn_relu_fwd / _bwd, csrc/bn_cl.cu).  `bn_act(bn, x, identity, relu)` keeps nn.BatchNorm2d as the owner of the
+parameters and running statistics (state_dict unchanged) and only replaces the arithmetic; anything the kernels do not
+cover (eval mode, CPU tensors, channel counts that are not multiples of 4, cumulative-average momentum) takes the plain
+torch path `relu(bn(x) + identity)`."""
+import os
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+enabled = os.environ.get("MVF_FUSED_BN", "1") != "0"
+launches = {"bn_fwd": 0, "bn_bwd": 0}
+_ws = {}
+
+
+def _workspace(dev, n):
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _ws.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(max(n, 1 << 18), device=dev, dtype=torch.float32)
+        _ws[key] = ws
+    return ws
+
+
+def _dense_cl(t):
+    B, C, H, W = t.shape
+    if t.dtype != torch.float32:
+        t = t.float()
+    if tuple(t.stride()) != (H * W * C, 1, W * C, C):
+        out = torch.empty(B, H, W, C, device=t.device, dtype=torch.float32).permute(0, 3, 1, 2)
+        out.copy_(t)
+        t = out
+    return t
+
+
+class _BNAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, identity, weight, bias, running_mean, running_var, eps, momentum, relu):
+        x = _dense_cl(x)
+        B, C, H, W = x.shape
+        P = B * H * W
+        if identity is not None:
+            identity = _dense_cl(identity)
+        y = torch.empty(B, H, W, C, device=x.device, dtype=torch.float32).permute(0, 3, 1, 2)
+        mean = torch.empty(C, device=x.device, dtype=torch.float32)
+        invstd = torch.empty(C, device=x.device, dtype=torch.float32)
+        L = _lib.lib()
+        ws = _workspace(x.device, L.mvf_bn_workspace_floats(P, C))
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        launches["bn_fwd"] += 1
+        _lib.check(L.mvf_bn_relu_fwd(x.data_ptr(), None if identity is None else identity.data_ptr(), y.data_ptr(), weight.data_ptr(),
+                                     bias.data_ptr(), None if running_mean is None else running_mean.data_ptr(),
+                                     None if running_var is None else running_var.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), P, C, eps, momentum, 1 if relu else 0, st), "mvf_bn_relu_fwd")
+        ctx.save_for_backward(x, y, weight, mean, invstd)
+        ctx.relu, ctx.has_identity = relu, identity is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y, weight, mean, invstd = ctx.saved_tensors
+        B, C, H, W = x.shape
+        P = B * H * W
+        gy = _dense_cl(gy)
+        gx = torch.empty(B, H, W, C, device=x.device, dtype=torch.float32).permute(0, 3, 1, 2)
+        gid = torch.empty(B, H, W, C, device=x.device, dtype=torch.float32).permute(0, 3, 1, 2) if (
+            ctx.has_identity and ctx.needs_input_grad[1]) else None
+        dgamma = torch.empty(C, device=x.device, dtype=torch.float32)
+        dbeta = torch.empty(C, device=x.device, dtype=torch.float32)
+        L = _lib.lib()
+        ws = _workspace(x.device, L.mvf_bn_workspace_floats(P, C))
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        launches["bn_bwd"] += 1
+        _lib.check(L.mvf_bn_relu_bwd(x.data_ptr(), gy.data_ptr(), y.data_ptr(), weight.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                     gx.data_ptr(), None if gid is None else gid.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), P, C, 1 if ctx.relu else 0, st), "mvf_bn_relu_bwd")
+        return gx, gid, dgamma, dbeta, None, None, None, None, None
+
+
+def usable(bn, x):
+    return (enabled and bn.training and x.is_cuda and x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[1] <= 1024 and
+            bn.affine and bn.momentum is not None and x.dtype == torch.float32)
+
+
+def bn_act(bn, x, identity=None, relu=True):
+    """relu(bn(x) + identity) with nn.BatchNorm2d `bn` (its parameters / buffers are used and updated in place)."""
+    if usable(bn, x):
+        if bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        rm, rv = (bn.running_mean, bn.running_var) if bn.track_running_stats else (None, None)
+        return _BNAct.apply(x, identity, bn.weight, bn.bias, rm, rv, float(bn.eps), float(bn.momentum), bool(relu))
+    y = bn(x)
+    if identity is not None:
+        y = y + identity
+    return F.relu(y) if relu else y

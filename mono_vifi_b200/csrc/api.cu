@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 
+#include "bn_cl.cuh"
 #include "conv_tc.cuh"
 #include "f1.cuh"
 #include "ops.cuh"
@@ -316,6 +317,28 @@ int mvf_maxpool3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int 
 int mvf_maxpool3s2_bwd(const float* grad_y, const unsigned char* idx, float* grad_x, int B, int C, int H, int W, void* stream) {
     if (!grad_y || !idx || !grad_x || B <= 0 || C <= 0 || (C % 4) || H < 2 || W < 2) return fail(MVF_ERR_INVALID, "mvf_maxpool3s2_bwd: bad argument (C % 4 == 0)");
     MVF_RUN("mvf_maxpool3s2_bwd", mvf::maxpool3s2_bwd(grad_y, idx, grad_x, B, C, H, W, (cudaStream_t)stream));
+}
+
+/* ---- fused BatchNorm2d (training) + residual add + ReLU, channels-last ------------------------------------------- */
+size_t mvf_bn_workspace_floats(long long P, int C) { return (P > 0 && C > 0 && C % 4 == 0 && C <= 1024) ? mvf::bn_workspace_floats(P, C) : 0; }
+int mvf_bn_relu_fwd(const float* x, const float* identity, float* y, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float* save_mean, float* save_invstd, float* workspace, size_t workspace_floats, long long P,
+                    int C, float eps, float momentum, int relu, void* stream) {
+    if (!x || !y || !gamma || !beta || !save_mean || !save_invstd || !workspace || P <= 0 || C <= 0 || (C % 4) || C > 1024)
+        return fail(MVF_ERR_INVALID, "mvf_bn_relu_fwd: bad argument (C % 4 == 0, C <= 1024)");
+    if (workspace_floats < mvf::bn_workspace_floats(P, C)) return fail(MVF_ERR_WORKSPACE, "mvf_bn_relu_fwd: workspace too small");
+    MVF_RUN("mvf_bn_relu_fwd", mvf::bn_forward(x, identity, y, gamma, beta, running_mean, running_var, save_mean, save_invstd, workspace,
+                                               P, C, eps, momentum, relu, (cudaStream_t)stream));
+}
+int mvf_bn_relu_bwd(const float* x, const float* grad_y, const float* y, const float* gamma, const float* save_mean,
+                    const float* save_invstd, float* grad_x, float* grad_identity, float* grad_gamma, float* grad_beta,
+                    float* workspace, size_t workspace_floats, long long P, int C, int relu, void* stream) {
+    if (!x || !grad_y || !gamma || !save_mean || !save_invstd || !grad_x || !grad_gamma || !grad_beta || !workspace || P <= 0 ||
+        C <= 0 || (C % 4) || C > 1024 || (relu && !y))
+        return fail(MVF_ERR_INVALID, "mvf_bn_relu_bwd: bad argument (C % 4 == 0, C <= 1024)");
+    if (workspace_floats < mvf::bn_workspace_floats(P, C)) return fail(MVF_ERR_WORKSPACE, "mvf_bn_relu_bwd: workspace too small");
+    MVF_RUN("mvf_bn_relu_bwd", mvf::bn_backward(x, grad_y, y, gamma, save_mean, save_invstd, grad_x, grad_identity, grad_gamma, grad_beta,
+                                                workspace, P, C, relu, (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,223 @@
+// Training-mode BatchNorm2d fused with the ReLU (and the residual add) that follows it in the ResNet blocks, on dense
+// channels-last tensors [P = B*H*W pixels][C channels] (torchvision BasicBlock / Bottleneck as used by
+// networks/monodepth2.py:16-31 and networks/posenet.py:10-52; hrnet_encoder.py:58-139):
+//
+//   forward : y = relu( (x - mean_c) * rsqrt(var_c + eps) * gamma_c + beta_c  [+ identity] )
+//   backward: g = grad_y * (y > 0);  d_beta = sum g;  d_gamma = sum g * xhat;
+//             grad_x = gamma * invstd * (g - d_beta / P - xhat * d_gamma / P);  grad_identity = g
+//
+// HBM-bound: the forward reads x twice (statistics, apply) [+ identity once] and writes y once; the backward reads
+// (grad_y, y, x) twice and writes grad_x [+ grad_identity].  Per-channel sums are accumulated per CTA, written to a
+// workspace and added in a fixed order by a small finalize kernel (double precision): bitwise deterministic.
+#include "bn_cl.cuh"
+
+namespace mvf {
+namespace {
+
+constexpr int NT = 256;
+
+// partial[block][0][c], partial[block][1][c]: two per-channel sums of this block's pixel share
+template <bool BWD>
+__global__ void __launch_bounds__(NT) bn_partial_kernel(const float4* __restrict__ x, const float4* __restrict__ gy,
+                                                        const float4* __restrict__ y, const float* __restrict__ mean,
+                                                        const float* __restrict__ invstd, float* __restrict__ partial, long long P,
+                                                        int C4, int relu) {
+    extern __shared__ float4 red[];  // [rows][C4] x 2
+    const int rows = NT / C4 > 0 ? NT / C4 : 1;  // threads are (row, channel group); C4 <= NT is checked by the host
+    const int c = threadIdx.x % C4, r = threadIdx.x / C4;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    if (r < rows) {
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f), is = m;
+        if (BWD) {
+            m = *reinterpret_cast<const float4*>(mean + 4 * c);
+            is = *reinterpret_cast<const float4*>(invstd + 4 * c);
+        }
+        // four pixels per trip so that four (twelve in the backward) independent 16-byte loads are in flight per thread
+        const long long step = (long long)gridDim.x * rows;
+        for (long long p0 = (long long)blockIdx.x * rows + r; p0 < P; p0 += 4 * step) {
+            float4 v[4], g[4], o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long p = p0 + u * step;
+                const bool ok = p < P;
+                v[u] = ok ? __ldg(x + p * C4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (BWD) {
+                    g[u] = ok ? __ldg(gy + p * C4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    o[u] = (ok && relu) ? __ldg(y + p * C4 + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (!ok) v[u] = m;  // xhat = 0
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!BWD) {
+                    s0.x += v[u].x; s0.y += v[u].y; s0.z += v[u].z; s0.w += v[u].w;
+                    s1.x = fmaf(v[u].x, v[u].x, s1.x); s1.y = fmaf(v[u].y, v[u].y, s1.y);
+                    s1.z = fmaf(v[u].z, v[u].z, s1.z); s1.w = fmaf(v[u].w, v[u].w, s1.w);
+                } else {
+                    float4 q = g[u];
+                    q.x = o[u].x > 0.f ? q.x : 0.f; q.y = o[u].y > 0.f ? q.y : 0.f; q.z = o[u].z > 0.f ? q.z : 0.f; q.w = o[u].w > 0.f ? q.w : 0.f;
+                    s0.x += q.x; s0.y += q.y; s0.z += q.z; s0.w += q.w;
+                    s1.x = fmaf(q.x, (v[u].x - m.x) * is.x, s1.x); s1.y = fmaf(q.y, (v[u].y - m.y) * is.y, s1.y);
+                    s1.z = fmaf(q.z, (v[u].z - m.z) * is.z, s1.z); s1.w = fmaf(q.w, (v[u].w - m.w) * is.w, s1.w);
+                }
+            }
+        }
+        red[r * C4 + c] = s0;
+        red[(rows + r) * C4 + c] = s1;
+    }
+    __syncthreads();
+    if (threadIdx.x < C4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        for (int q = 0; q < rows; ++q) {  // fixed order
+            const float4 u = red[q * C4 + threadIdx.x], w = red[(rows + q) * C4 + threadIdx.x];
+            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+            b.x += w.x; b.y += w.y; b.z += w.z; b.w += w.w;
+        }
+        float4* out = reinterpret_cast<float4*>(partial) + (size_t)blockIdx.x * 2 * C4;
+        out[threadIdx.x] = a;
+        out[C4 + threadIdx.x] = b;
+    }
+}
+
+// forward: mean / biased variance -> (mean, invstd) saved for backward, running statistics updated as nn.BatchNorm2d does
+__global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int nblocks, int C, long long P, float eps, float momentum,
+                                       float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
+                                       float* __restrict__ running_var) {
+    // one warp per channel: lane l adds blocks l, l+32, ...; a fixed shuffle tree combines the lanes
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= C) return;
+    double s = 0.0, ss = 0.0;
+    for (int b = lane; b < nblocks; b += 32) {
+        s += (double)partial[(size_t)b * 2 * C + c];
+        ss += (double)partial[(size_t)b * 2 * C + C + c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane != 0) return;
+    const double m = s / (double)P;
+    double var = ss / (double)P - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        const double unbiased = P > 1 ? var * (double)P / (double)(P - 1) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    }
+}
+
+// backward: d_beta = sum g, d_gamma = sum g * xhat
+__global__ void bn_finalize_bwd_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= C) return;
+    double s = 0.0, ss = 0.0;
+    for (int b = lane; b < nblocks; b += 32) {
+        s += (double)partial[(size_t)b * 2 * C + c];
+        ss += (double)partial[(size_t)b * 2 * C + C + c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane != 0) return;
+    dbeta[c] = (float)s;
+    dgamma[c] = (float)ss;
+}
+
+__global__ void bn_apply_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ identity, float4* __restrict__ y,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, long long total4, int C4, int relu) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        const float4 m = *reinterpret_cast<const float4*>(mean + 4 * c), is = *reinterpret_cast<const float4*>(invstd + 4 * c);
+        const float4 ga = *reinterpret_cast<const float4*>(gamma + 4 * c), be = *reinterpret_cast<const float4*>(beta + 4 * c);
+        const float4 v = __ldg(x + i);
+        float4 o;
+        o.x = fmaf((v.x - m.x) * is.x, ga.x, be.x); o.y = fmaf((v.y - m.y) * is.y, ga.y, be.y);
+        o.z = fmaf((v.z - m.z) * is.z, ga.z, be.z); o.w = fmaf((v.w - m.w) * is.w, ga.w, be.w);
+        if (identity) {
+            const float4 d = __ldg(identity + i);
+            o.x += d.x; o.y += d.y; o.z += d.z; o.w += d.w;
+        }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        y[i] = o;
+    }
+}
+
+__global__ void bn_apply_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gy, const float4* __restrict__ y,
+                                    float4* __restrict__ gx, float4* __restrict__ gid, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ dgamma,
+                                    const float* __restrict__ dbeta, long long total4, int C4, float inv_P, int relu) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        const float4 m = *reinterpret_cast<const float4*>(mean + 4 * c), is = *reinterpret_cast<const float4*>(invstd + 4 * c);
+        const float4 ga = *reinterpret_cast<const float4*>(gamma + 4 * c);
+        const float4 dg = *reinterpret_cast<const float4*>(dgamma + 4 * c), db = *reinterpret_cast<const float4*>(dbeta + 4 * c);
+        const float4 v = __ldg(x + i);
+        float4 g = __ldg(gy + i);
+        if (relu) {
+            const float4 o = __ldg(y + i);
+            g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+        }
+        if (gid) gid[i] = g;
+        float4 r;
+        r.x = ga.x * is.x * (g.x - db.x * inv_P - (v.x - m.x) * is.x * dg.x * inv_P);
+        r.y = ga.y * is.y * (g.y - db.y * inv_P - (v.y - m.y) * is.y * dg.y * inv_P);
+        r.z = ga.z * is.z * (g.z - db.z * inv_P - (v.z - m.z) * is.z * dg.z * inv_P);
+        r.w = ga.w * is.w * (g.w - db.w * inv_P - (v.w - m.w) * is.w * dg.w * inv_P);
+        gx[i] = r;
+    }
+}
+
+int partial_blocks(long long P, int C4) {
+    const int rows = NT / C4 > 0 ? NT / C4 : 1;
+    long long nb = (P + (long long)rows * 16 - 1) / ((long long)rows * 16);  // at least ~16 pixels per thread
+    if (nb > 148 * 2) nb = 148 * 2;
+    if (nb < 1) nb = 1;
+    return (int)nb;
+}
+int apply_blocks(long long total4) {
+    long long nb = (total4 + NT - 1) / NT;
+    return (int)(nb > 148 * 16 ? 148 * 16 : (nb < 1 ? 1 : nb));
+}
+
+}  // namespace
+
+size_t bn_workspace_floats(long long P, int C) { return (size_t)partial_blocks(P, C / 4) * 2 * C; }
+
+cudaError_t bn_forward(const float* x, const float* identity, float* y, const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, float* save_mean, float* save_invstd, float* workspace, long long P, int C, float eps,
+                       float momentum, int relu, cudaStream_t st) {
+    const int C4 = C / 4, nb = partial_blocks(P, C4);
+    const int rows = NT / C4 > 0 ? NT / C4 : 1;
+    bn_partial_kernel<false><<<nb, NT, 2 * rows * C4 * sizeof(float4), st>>>((const float4*)x, nullptr, nullptr, nullptr, nullptr,
+                                                                            workspace, P, C4, 0);
+    bn_finalize_fwd_kernel<<<(C + 3) / 4, 128, 0, st>>>(workspace, nb, C, P, eps, momentum, save_mean, save_invstd, running_mean,
+                                                          running_var);
+    const long long total4 = P * C4;
+    bn_apply_fwd_kernel<<<apply_blocks(total4), NT, 0, st>>>((const float4*)x, (const float4*)identity, (float4*)y, save_mean,
+                                                           save_invstd, gamma, beta, total4, C4, relu);
+    return cudaGetLastError();
+}
+
+cudaError_t bn_backward(const float* x, const float* gy, const float* y, const float* gamma, const float* save_mean,
+                        const float* save_invstd, float* gx, float* gidentity, float* dgamma, float* dbeta, float* workspace,
+                        long long P, int C, int relu, cudaStream_t st) {
+    const int C4 = C / 4, nb = partial_blocks(P, C4);
+    const int rows = NT / C4 > 0 ? NT / C4 : 1;
+    bn_partial_kernel<true><<<nb, NT, 2 * rows * C4 * sizeof(float4), st>>>((const float4*)x, (const float4*)gy, (const float4*)y,
+                                                                           save_mean, save_invstd, workspace, P, C4, relu);
+    bn_finalize_bwd_kernel<<<(C + 3) / 4, 128, 0, st>>>(workspace, nb, C, dgamma, dbeta);
+    const long long total4 = P * C4;
+    bn_apply_bwd_kernel<<<apply_blocks(total4), NT, 0, st>>>((const float4*)x, (const float4*)gy, (const float4*)y, (float4*)gx,
+                                                           (float4*)gidentity, save_mean, save_invstd, gamma, dgamma, dbeta, total4,
+                                                           C4, (float)(1.0 / (double)P), relu);
+    return cudaGetLastError();
+}
+
+}  // namespace mvf

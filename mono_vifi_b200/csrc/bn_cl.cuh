@@ -1,0 +1,14 @@
+// Fused training-mode BatchNorm2d (+ residual add) + ReLU on dense channels-last tensors (see bn_cl.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace mvf {
+size_t bn_workspace_floats(long long P, int C);
+cudaError_t bn_forward(const float* x, const float* identity, float* y, const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, float* save_mean, float* save_invstd, float* workspace, long long P, int C, float eps,
+                       float momentum, int relu, cudaStream_t st);
+cudaError_t bn_backward(const float* x, const float* gy, const float* y, const float* gamma, const float* save_mean,
+                        const float* save_invstd, float* gx, float* gidentity, float* dgamma, float* dbeta, float* workspace,
+                        long long P, int C, int relu, cudaStream_t st);
+}  // namespace mvf

@@ -325,16 +325,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
                 for (int tp = 0; tp < taps; ++tp) {
                     if (!p.b_resident) mbar_wait(&b_full[bs], bph);
                     tc_fence_after();
-                    const uint32_t b_lo = (smB_u + (uint32_t)((p.b_resident ? tp * p.n_cblk + cb : bs) * B_STAGE_BYTES)) >> 4;
+                    // lo word = start address (14 bits) below the LBO field: advancing is a plain 32-bit add
+                    const uint32_t b_lo = ((smB_u + (uint32_t)((p.b_resident ? tp * p.n_cblk + cb : bs) * B_STAGE_BYTES)) >> 4) | (uint32_t)desc_hi;
+                    const uint64_t d_up = desc_hi & 0xFFFFFFFF00000000ull;
                     if (elect_one()) {
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) {
                             if (p.dbg & 4) break;
-                            const uint32_t a_lo = (a_base + (uint32_t)((mt * p.TR + kh) * p.P + kw) * 128u) >> 4;
+                            const uint32_t a_lo = ((a_base + (uint32_t)((mt * p.TR + kh) * p.P + kw) * 128u) >> 4) | (uint32_t)desc_hi;
 #pragma unroll
                             for (int kg = 0; kg < KGROUPS; ++kg)
-                                umma_tf32(d_base + (uint32_t)(mt * N_TILE), desc_hi | (uint64_t)(a_lo + 2 * kg),
-                                          desc_hi | (uint64_t)(b_lo + 2 * kg), idesc, (cb > 0 || tp > 0 || kg > 0) ? 1u : 0u);
+                                umma_tf32(d_base + (uint32_t)(mt * N_TILE), d_up | (uint64_t)(a_lo + 2 * kg),
+                                          d_up | (uint64_t)(b_lo + 2 * kg), idesc, (cb > 0 || tp > 0 || kg > 0) ? 1u : 0u);
                         }
                         if (!p.b_resident) umma_commit(&b_empty[bs]);
                     }

@@ -122,16 +122,21 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
         for (int it = 0; it < n_iters; ++it) {
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
-            const uint32_t a_lo = (smem_u + (uint32_t)(s * p.stage_bytes)) >> 4;
-            const uint32_t b_lo = a_lo + ((uint32_t)p.a_bytes >> 4);
+            // descriptor = {hi word (constant), lo word}: the lo word holds the start address (14 bits) below the LBO field,
+            // so stepping through the stage is a plain 32-bit add on it
+            const uint32_t a_lo = ((smem_u + (uint32_t)(s * p.stage_bytes)) >> 4) | (uint32_t)a_hi;
+            const uint32_t b_lo = (((smem_u + (uint32_t)(s * p.stage_bytes)) >> 4) + ((uint32_t)p.a_bytes >> 4)) | (uint32_t)b_hi;
+            const uint64_t a_up = a_hi & 0xFFFFFFFF00000000ull, b_up = b_hi & 0xFFFFFFFF00000000ull;
             if (elect_one()) {
                 int kh = 0, kw = 0;
                 for (int t = 0; t < taps; ++t) {
                     // tap t: its own box, or the shared patch shifted by kh rows and kw pixels (whole 128-byte rows)
                     const uint32_t bt = p.shared_patch ? b_lo + (uint32_t)((kh * p.pwx + kw) * 8) : b_lo + (uint32_t)(t * kp * 8);
+                    const uint32_t dcol = tmem_d + (uint32_t)(t * N_TILE);
+#pragma unroll 4
                     for (int kk = 0; kk < kmma; ++kk)
-                        umma_tf32(tmem_d + (uint32_t)(t * N_TILE), a_hi | (uint64_t)(a_lo + kk * 64), b_hi | (uint64_t)(bt + kk * 64),
-                                  idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                        umma_tf32(dcol, a_up | (uint64_t)(a_lo + kk * 64), b_up | (uint64_t)(bt + kk * 64), idesc,
+                                  (it > 0 || kk > 0) ? 1u : 0u);
                     if (++kw == p.KW) { kw = 0; ++kh; }
                 }
                 umma_commit(&empty_bar[s]);

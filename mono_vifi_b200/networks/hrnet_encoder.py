@@ -6,6 +6,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..bn_act import bn_act
 from ..conv import Conv2d
 
 # (modules, blocks per branch, channels per branch, block type) for stages 1..4 of HRNet-W18  (hrnet_config.py:119-153)
@@ -38,8 +39,8 @@ class BasicUnit(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
-        y = self.bn2(self.conv2(self.relu(self.bn1(self.conv1(x)))))
-        return self.relu(y + (x if self.downsample is None else self.downsample(x)))
+        identity = x if self.downsample is None else self.downsample(x)
+        return bn_act(self.bn2, self.conv2(bn_act(self.bn1, self.conv1(x))), identity)
 
 
 class BottleneckUnit(nn.Module):
@@ -58,10 +59,9 @@ class BottleneckUnit(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
-        y = self.relu(self.bn1(self.conv1(x)))
-        y = self.relu(self.bn2(self.conv2(y)))
-        y = self.bn3(self.conv3(y))
-        return self.relu(y + (x if self.downsample is None else self.downsample(x)))
+        identity = x if self.downsample is None else self.downsample(x)
+        y = bn_act(self.bn2, self.conv2(bn_act(self.bn1, self.conv1(x))))
+        return bn_act(self.bn3, self.conv3(y), identity)
 
 
 _UNITS = {"basic": BasicUnit, "bottleneck": BottleneckUnit}

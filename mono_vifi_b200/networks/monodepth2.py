@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 
 from ..layers import ConvBlock, Conv3x3, upsample
+from ..bn_act import bn_act
 from .resnet import ResNet, load_imagenet
 
 
@@ -27,8 +28,7 @@ class DepthEncoder(nn.Module):
         self.features = []
         x = (input_image - 0.45) / 0.225
         x = self.encoder.conv1(x)
-        x = self.encoder.bn1(x)
-        self.features.append(self.encoder.relu(x))
+        self.features.append(bn_act(self.encoder.bn1, x))  # bn1 + relu
         self.features.append(self.encoder.layer1(self.encoder.maxpool(self.features[-1])))
         self.features.append(self.encoder.layer2(self.features[-1]))
         self.features.append(self.encoder.layer3(self.features[-1]))

@@ -6,6 +6,7 @@ import torch
 import torch.nn as nn
 
 from ..conv import Conv2d
+from ..bn_act import bn_act
 from .resnet import ResNet, load_imagenet
 
 
@@ -39,8 +40,7 @@ class ResnetEncoder(nn.Module):
         self.features = []
         x = (input_image - 0.45) / 0.225
         x = self.encoder.conv1(x)
-        x = self.encoder.bn1(x)
-        self.features.append(self.encoder.relu(x))
+        self.features.append(bn_act(self.encoder.bn1, x))  # bn1 + relu
         self.features.append(self.encoder.layer1(self.encoder.maxpool(self.features[-1])))
         self.features.append(self.encoder.layer2(self.features[-1]))
         self.features.append(self.encoder.layer3(self.features[-1]))

@@ -4,6 +4,7 @@ Used by networks/monodepth2.py (DepthEncoder) and networks/posenet.py (ResnetEnc
 Reference: monodepth2.py:16-31, posenet.py:10-52 (both wrap torchvision.models.resnet)."""
 import torch.nn as nn
 
+from ..bn_act import bn_act
 from ..conv import Conv2d
 from ..decoder_ops import MaxPool3s2
 
@@ -22,13 +23,9 @@ class BasicBlock(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        identity = x
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.bn2(self.conv2(out))
-        if self.downsample is not None:
-            identity = self.downsample(x)
-        out += identity
-        return self.relu(out)
+        identity = x if self.downsample is None else self.downsample(x)
+        out = bn_act(self.bn1, self.conv1(x))                        # bn + relu in one pass
+        return bn_act(self.bn2, self.conv2(out), identity)           # bn + residual add + relu in one pass
 
 
 class Bottleneck(nn.Module):
@@ -47,14 +44,10 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        identity = x
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
-        if self.downsample is not None:
-            identity = self.downsample(x)
-        out += identity
-        return self.relu(out)
+        identity = x if self.downsample is None else self.downsample(x)
+        out = bn_act(self.bn1, self.conv1(x))
+        out = bn_act(self.bn2, self.conv2(out))
+        return bn_act(self.bn3, self.conv3(out), identity)
 
 
 _CFG = {18: (BasicBlock, [2, 2, 2, 2]), 34: (BasicBlock, [3, 4, 6, 3]), 50: (Bottleneck, [3, 4, 6, 3]),

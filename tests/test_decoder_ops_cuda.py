@@ -70,3 +70,43 @@ def test_maxpool3s2_matches_torch(shape):
     y.backward(gy)
     ref.backward(gy)
     assert torch.allclose(x.grad, xr.grad, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", [(2, 64, 12, 20, True, True), (3, 128, 6, 10, False, True), (2, 16, 9, 7, True, False),
+                                  (12, 64, 96, 320, True, True), (1, 512, 6, 20, False, True), (2, 144, 6, 10, True, True)])
+def test_fused_bn_add_relu_matches_torch(case):
+    """relu(bn(x) + identity) in training mode: output, running statistics and all gradients against torch in fp64"""
+    import torch
+    from mono_vifi_b200 import bn_act
+    B, C, H, W, with_id, relu = case
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = (2.0 * torch.randn(B, C, H, W, device="cuda", generator=g) + 0.5).requires_grad_(True)
+    idn = torch.randn(B, C, H, W, device="cuda", generator=g).requires_grad_(True) if with_id else None
+    bn = torch.nn.BatchNorm2d(C).cuda().train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.3)
+    ref_bn = torch.nn.BatchNorm2d(C).cuda().double().train()
+    ref_bn.load_state_dict({k: (v.double() if v.dtype.is_floating_point else v) for k, v in bn.state_dict().items()})
+    before = dict(bn_act.launches)
+    y = bn_act.bn_act(bn, x, idn, relu)
+    assert bn_act.launches["bn_fwd"] == before["bn_fwd"] + 1
+    xr = x.detach().double().requires_grad_(True)
+    ir = idn.detach().double().requires_grad_(True) if with_id else None
+    yr = ref_bn(xr)
+    if with_id:
+        yr = yr + ir
+    if relu:
+        yr = torch.relu(yr)
+    assert (y.double() - yr).abs().max().item() <= 2e-5 * max(1.0, yr.abs().max().item())
+    assert torch.allclose(bn.running_mean.double(), ref_bn.running_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(bn.running_var.double(), ref_bn.running_var, rtol=1e-5, atol=1e-6)
+    assert int(bn.num_batches_tracked) == int(ref_bn.num_batches_tracked) == 1
+    gy = torch.randn(y.shape, device="cuda", generator=g)
+    y.backward(gy)
+    yr.backward(gy.double())
+    pairs = [(x.grad, xr.grad), (bn.weight.grad, ref_bn.weight.grad), (bn.bias.grad, ref_bn.bias.grad)]
+    if with_id:
+        pairs.append((idn.grad, ir.grad))
+    for got, want in pairs:
+        assert (got.double() - want).abs().max().item() <= 1e-4 * max(1e-3, want.abs().max().item())
