@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--cpu-batch", type=int, default=2, help="bounded CPU sample: images per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-optimizer", action="store_true", help="torch clip_grad_norm_ + AdamW instead of the fused flat-arena kernels")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--conv-backend", default=os.environ.get("MVF_CONV_BACKEND", "tcgen05"), choices=["tcgen05", "cudnn"])
     return ap.parse_args()
@@ -209,7 +210,8 @@ def run_ours(args):
     conv.set_backend(args.conv_backend)
     opt = TR.Options(batch_size=args.batch, height=args.height, width=args.width)
     torch.manual_seed(1234)
-    step = TR.TrainStep(opt, dev, distributed=(world > 1), capturable=not args.no_graph)
+    step = TR.TrainStep(opt, dev, distributed=(world > 1), capturable=not args.no_graph,
+                        fused_optimizer=not args.torch_optimizer)
     step.train()
     ddp.broadcast_parameters(step.params)
     # two distinct synthetic batches per rank, rotated, in pinned host memory and (for `value`) resident in HBM
@@ -336,6 +338,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "per_gpu_batch": args.batch, "global_batch": args.batch * world,
                        "height": args.height, "width": args.width, "parallelism": "dp%d" % world,
                        "launch": graph_note,
+                       "optimizer": "torch clip_grad_norm_ + AdamW" if args.torch_optimizer else "fused clip + AdamW over flat arenas (mvf_adamw_step)",
                        "conv_backend": conv.get_backend(), "conv_calls_per_step": conv_calls,
                        "conv_kernel_launches_per_step": conv_launches,
                        "l2": "working set (activations, several GB) is far larger than the 126 MB L2; inputs rotate between two batches"},

@@ -187,6 +187,17 @@ int mvf_bn_relu_bwd(const float* x, const float* grad_y, const float* y, const f
                     const float* save_invstd, float* grad_x, float* grad_identity, float* grad_gamma, float* grad_beta,
                     float* workspace, size_t workspace_floats, long long P, int C, int relu, void* stream);
 
+/* ---- fused torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.step over ONE flat fp32 arena (train.py:661-666) --------
+ * params / grads / exp_avg / exp_avg_sq: n floats each, 16-byte aligned.  state[2] (device): {step count, last gradient
+ * norm}; the step count is read and incremented on the device, so the call can be recorded into a CUDA graph.
+ * max_norm <= 0 disables clipping.  workspace: mvf_adamw_workspace_bytes() bytes of scratch (gradient-norm partials,
+ * added in a fixed order).  Same arithmetic as torch's (decoupled weight decay, bias-corrected moments, eps outside the
+ * square root). */
+size_t mvf_adamw_workspace_bytes(void);
+int mvf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,
+                   void* workspace, size_t workspace_bytes, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float max_norm, void* stream);
+
 /* device self-test: q_sequence[i] = the kernels' shared-reciprocal division of a[i] by b[i], q_ieee[i] = the
  * IEEE quotient (div.rn.f32); the two must be bit-identical for operands in the normal range. */
 int mvf_selftest_division(const float* a, const float* b, float* q_sequence, float* q_ieee, size_t n, void* stream);

@@ -9,6 +9,7 @@
 #include "f1.cuh"
 #include "ops.cuh"
 #include "ops_cl.cuh"
+#include "optim.cuh"
 
 namespace {
 thread_local char g_err[512] = "";
@@ -339,6 +340,19 @@ int mvf_bn_relu_bwd(const float* x, const float* grad_y, const float* y, const f
     if (workspace_floats < mvf::bn_workspace_floats(P, C)) return fail(MVF_ERR_WORKSPACE, "mvf_bn_relu_bwd: workspace too small");
     MVF_RUN("mvf_bn_relu_bwd", mvf::bn_backward(x, grad_y, y, gamma, save_mean, save_invstd, grad_x, grad_identity, grad_gamma, grad_beta,
                                                 workspace, P, C, relu, (cudaStream_t)stream));
+}
+
+/* ---- fused clip_grad_norm_ + AdamW over a flat arena -------------------------------------------------------------- */
+size_t mvf_adamw_workspace_bytes(void) { return mvf::adamw_workspace_bytes(); }
+int mvf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,
+                   void* workspace, size_t workspace_bytes, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float max_norm, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !state || !workspace || n <= 0) return fail(MVF_ERR_INVALID, "mvf_adamw_step: bad argument");
+    if (workspace_bytes < mvf::adamw_workspace_bytes()) return fail(MVF_ERR_WORKSPACE, "mvf_adamw_step: workspace too small");
+    if ((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) != 0)
+        return fail(MVF_ERR_INVALID, "mvf_adamw_step: arenas must be 16-byte aligned");
+    MVF_RUN("mvf_adamw_step", mvf::adamw_step(params, grads, exp_avg, exp_avg_sq, n, state, workspace, lr, beta1, beta2, eps,
+                                              weight_decay, max_norm, (cudaStream_t)stream));
 }
 
 }  // extern "C"

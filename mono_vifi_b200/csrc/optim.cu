@@ -1,0 +1,105 @@
+// Gradient clipping + AdamW over ONE flat fp32 arena (parameters, gradients, both moments): SURVEY.md 8(f) item 1.
+// Replaces torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.step (train.py:661-666), which walk ~200 tensors with a
+// dozen multi-tensor launches, by two passes over the arena:
+//   1. sum of squares of the gradient (per-CTA partials, fixed-order final sum -> deterministic)
+//   2. clip coefficient min(1, max_norm / (norm + 1e-6)) and the AdamW update, step counter kept on the device so the
+//      whole thing can be recorded into a CUDA graph.
+// HBM-bound: pass 1 reads 4 B/param, pass 2 reads 16 and writes 12 B/param.
+#include "optim.cuh"
+
+namespace mvf {
+namespace {
+
+constexpr int NT = 256;
+constexpr int NB_NORM = 296;  // 2 CTAs per SM
+
+__global__ void __launch_bounds__(NT) sumsq_partial_kernel(const float4* __restrict__ g, long long n4, const float* __restrict__ tail,
+                                                           int ntail, double* __restrict__ partial) {
+    double acc = 0.0;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) {
+        const float4 v = __ldg(g + i);
+        a0 = fmaf(v.x, v.x, a0); a1 = fmaf(v.y, v.y, a1); a2 = fmaf(v.z, v.z, a2); a3 = fmaf(v.w, v.w, a3);
+    }
+    acc = (double)a0 + (double)a1 + (double)a2 + (double)a3;
+    if (blockIdx.x == 0 && threadIdx.x < ntail) acc += (double)tail[threadIdx.x] * (double)tail[threadIdx.x];
+    __shared__ double red[NT];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = NT / 2; s > 0; s >>= 1) {  // fixed tree
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+// state[0] = step count (float), state[1] = last gradient norm (for logging)
+__global__ void __launch_bounds__(NT) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, const double* __restrict__ partial, int nb,
+                                                   float* __restrict__ state, float lr, float beta1, float beta2, float eps,
+                                                   float wd, float max_norm) {
+    __shared__ float s_coef, s_bc1, s_bc2s;
+    if (threadIdx.x == 0) {
+        double ss = 0.0;
+        for (int b = 0; b < nb; ++b) ss += partial[b];
+        const float norm = (float)sqrt(ss);
+        float coef = 1.0f;
+        if (max_norm > 0.f) coef = fminf(1.0f, max_norm / (norm + 1e-6f));  // clip_grad_norm_
+        const float t = state[0] + 1.0f;
+        s_coef = coef;
+        s_bc1 = 1.0f - powf(beta1, t);
+        s_bc2s = sqrtf(1.0f - powf(beta2, t));
+    }
+    __syncthreads();
+    const float coef = s_coef, step_size = lr / s_bc1, bc2s = s_bc2s;
+    const long long n4 = n / 4;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+        gg *= coef;
+        pp *= (1.0f - lr * wd);
+        mm = beta1 * mm + (1.0f - beta1) * gg;   // lerp form of torch: m + (g - m)(1 - beta1)
+        vv = beta2 * vv + (1.0f - beta2) * gg * gg;
+        const float denom = sqrtf(vv) / bc2s + eps;
+        pp -= step_size * (mm / denom);
+    };
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) {
+        float4 pp = p4[i], mm = m4[i], vv = v4[i];
+        const float4 gg = __ldg(g4 + i);
+        upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+        p4[i] = pp; m4[i] = mm; v4[i] = vv;
+    }
+    if (blockIdx.x == 0) {
+        const long long i = n4 * 4 + threadIdx.x;
+        if (i < n) upd(p[i], g[i], m[i], v[i]);
+    }
+}
+
+// bumps the step counter AFTER every CTA of adamw_kernel has read it (separate tiny launch on the same stream)
+__global__ void adamw_tick_kernel(float* state, const double* partial, int nb) {
+    double ss = 0.0;
+    for (int b = 0; b < nb; ++b) ss += partial[b];
+    state[0] += 1.0f;
+    state[1] = (float)sqrt(ss);
+}
+
+}  // namespace
+
+size_t adamw_workspace_bytes() { return NB_NORM * sizeof(double); }
+
+cudaError_t adamw_step(float* p, const float* g, float* m, float* v, long long n, float* state, void* workspace, float lr,
+                       float beta1, float beta2, float eps, float wd, float max_norm, cudaStream_t st) {
+    double* partial = reinterpret_cast<double*>(workspace);
+    const long long n4 = n / 4;
+    sumsq_partial_kernel<<<NB_NORM, NT, 0, st>>>(reinterpret_cast<const float4*>(g), n4, g + n4 * 4, (int)(n - n4 * 4), partial);
+    long long nb = (n4 + NT - 1) / NT;
+    if (nb > 148 * 8) nb = 148 * 8;
+    if (nb < 1) nb = 1;
+    adamw_kernel<<<(int)nb, NT, 0, st>>>(p, g, m, v, n, partial, NB_NORM, state, lr, beta1, beta2, eps, wd, max_norm);
+    adamw_tick_kernel<<<1, 1, 0, st>>>(state, partial, NB_NORM);
+    return cudaGetLastError();
+}
+
+}  // namespace mvf

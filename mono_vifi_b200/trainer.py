@@ -151,7 +151,7 @@ def multi_frame_losses(models, vfi, inputs, opt):
 class TrainStep:
     """zero_grad -> forward -> backward -> (all-reduce) -> clip -> AdamW  (train.py:656-666)."""
 
-    def __init__(self, opt, device, models=None, distributed=False, capturable=False):
+    def __init__(self, opt, device, models=None, distributed=False, capturable=False, fused_optimizer=None):
         self.opt, self.device = opt, device
         self.models = models if models is not None else build_models(opt, device)
         # the frozen VFI network of the multi-frame branch (train.py:210-216); not trained, not in the optimizer
@@ -163,10 +163,21 @@ class TrainStep:
                 if id(p) not in seen:
                     seen.add(id(p))
                     self.params.append(p)
-        # capturable: step counters live on the device so that the whole step can be recorded into a CUDA graph
-        self.optimizer = torch.optim.AdamW(self.params, lr=opt.learning_rate, weight_decay=opt.weight_decay,
-                                           capturable=bool(capturable and device.type == "cuda"))
-        self.reducer = FlatGradAllReduce(self.params) if distributed else None
+        # default on CUDA: clip + AdamW (+ the gradient all-reduce) over flat arenas, two kernel launches per step
+        # (optim.FlatAdamW); otherwise torch.optim.AdamW (capturable: step counters on the device for CUDA graphs)
+        if fused_optimizer is None:
+            fused_optimizer = device.type == "cuda"
+        self.flat = None
+        self.optimizer = None
+        self.reducer = None
+        if fused_optimizer:
+            from .optim import FlatAdamW
+            self.flat = FlatAdamW(self.params, lr=opt.learning_rate, weight_decay=opt.weight_decay,
+                                  max_norm=float(opt.clip_grad or 0.0), distributed=distributed)
+        else:
+            self.optimizer = torch.optim.AdamW(self.params, lr=opt.learning_rate, weight_decay=opt.weight_decay,
+                                               capturable=bool(capturable and device.type == "cuda"))
+            self.reducer = FlatGradAllReduce(self.params) if distributed else None
         # All training work runs on one dedicated (non-default) stream.  autograd binds each parameter's gradient
         # accumulator to the stream of its first use; binding them to the legacy default stream would make the step
         # impossible to record into a CUDA graph later (GraphedTrainStep).
@@ -177,7 +188,9 @@ class TrainStep:
             m.train()
 
     def forward_backward(self, inputs):
-        if self.reducer is not None:
+        if self.flat is not None:
+            self.flat.zero_grad()
+        elif self.reducer is not None:
             self.reducer.attach()  # zeroes the flat arena and points every .grad at its slice
         else:
             self.optimizer.zero_grad(set_to_none=True)
@@ -192,9 +205,12 @@ class TrainStep:
 
     def _step(self, inputs):
         out = self.forward_backward(inputs)
-        if self.opt.clip_grad is not None and self.opt.clip_grad > 0:
-            torch.nn.utils.clip_grad_norm_([p for p in self.params if p.grad is not None], self.opt.clip_grad)
-        self.optimizer.step()
+        if self.flat is not None:
+            self.flat.step()  # all-reduce (N > 1) + clip + AdamW
+        else:
+            if self.opt.clip_grad is not None and self.opt.clip_grad > 0:
+                torch.nn.utils.clip_grad_norm_([p for p in self.params if p.grad is not None], self.opt.clip_grad)
+            self.optimizer.step()
         loss = out["loss"].detach()
         for m in self.models.values():  # the reference's modules keep their last activations; drop the graph they hold
             if hasattr(m, "features"):
@@ -234,7 +250,7 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(self.stream)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        if step.reducer is None:
+        if step.reducer is None and step.optimizer is not None:
             step.optimizer.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.graph, stream=self.stream):
             self.static_loss = step(self.static_inputs)

@@ -171,3 +171,32 @@ def test_multi_frame_train_step_litemono_runs():
     assert all(np.isfinite(losses)) and abs(losses[-1] - losses[0]) < 0.1
     assert not torch.equal(w0, step.models["depth"].convs[("dispconv", 0)].conv.weight.detach())
     assert conv.stats["tcgen05"] > 0 and conv.stats["cudnn"] > 0
+
+
+def test_flat_adamw_matches_torch():
+    """clip + AdamW over the flat arena vs torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW, five steps"""
+    import torch
+    from mono_vifi_b200.optim import FlatAdamW
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    mk = lambda: torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.Tanh(), torch.nn.Linear(53, 11), torch.nn.Linear(11, 3)).to(dev)
+    a, b = mk(), mk()
+    b.load_state_dict(a.state_dict())
+    unused = torch.nn.Parameter(torch.randn(5, device=dev))      # never receives a gradient: must stay untouched
+    unused0 = unused.detach().clone()
+    ref = torch.optim.AdamW(a.parameters(), lr=1e-2, weight_decay=0.05)
+    flat = FlatAdamW(list(b.parameters()) + [unused], lr=1e-2, weight_decay=0.05, max_norm=0.5)
+    for it in range(5):
+        x = torch.randn(16, 37, device=dev)
+        ref.zero_grad(set_to_none=True)
+        (a(x) ** 2).sum().backward()
+        norm = torch.nn.utils.clip_grad_norm_(a.parameters(), 0.5)
+        ref.step()
+        flat.zero_grad()
+        (b(x) ** 2).sum().backward()
+        flat.step()
+        assert abs(float(flat.grad_norm) - float(norm)) <= 1e-4 * float(norm)
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            assert torch.allclose(pa, pb, rtol=2e-5, atol=2e-6), it
+    assert torch.equal(unused.detach(), unused0) and unused.grad is None
+    assert float(flat.state[0]) == 5.0
