@@ -278,8 +278,11 @@ def run_ours(args):
     stage = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    feeder = TR.HostFedRunner(run, host[0]) if run is not step else None
     e2.record()
     last = 0.0
+    if feeder is not None:
+        feeder.feed(host[0])                    # inside the timed region: every step's H2D is
     for i in range(args.steps):
         if run is step:
             buf = stage[i % 2]
@@ -287,7 +290,10 @@ def run_ours(args):
                 buf[k].copy_(v, non_blocking=True)
             last = float(step(buf))  # D2H read of the step's loss
         else:
-            last = float(run(host[i % 2]))  # H2D into the graph's static inputs, replay, D2H read of the loss
+            loss_t = feeder.run()               # step i on the staged batch (graph replay)
+            if i + 1 < args.steps:
+                feeder.feed(host[(i + 1) % 2])  # H2D of batch i+1 on the copy stream, overlapping step i
+            last = float(loss_t)                # D2H read of the step's loss (synchronises)
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3) / args.steps

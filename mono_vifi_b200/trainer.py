@@ -266,6 +266,44 @@ class GraphedTrainStep:
         return self.static_loss
 
 
+class HostFedRunner:
+    """End-to-end driver for batches that live in pinned HOST memory: the H2D copy of batch i+1 runs on a copy stream
+    while step i computes (two staging sets in HBM), the staged batch is moved into the graph's static inputs with one
+    device-to-device copy, and the loss of every step is read back.  `feed(batch)` enqueues the next host batch,
+    `run()` executes one step on the oldest staged batch and returns its loss as a Python float (D2H read)."""
+
+    def __init__(self, graphed_step, example_host_batch):
+        self.g = graphed_step
+        dev = graphed_step.step.device
+        self.dev = dev
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.stage = [{k: torch.empty_like(v, device=dev) for k, v in example_host_batch.items()} for _ in range(2)]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]   # H2D of the set finished
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]  # the set was copied into the static inputs
+        self.head = self.tail = 0
+        for e in self.consumed:
+            e.record(torch.cuda.current_stream(dev))
+
+    def feed(self, host_batch):
+        i = self.head % 2
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[i])
+            for k, v in host_batch.items():
+                self.stage[i][k].copy_(v, non_blocking=True)
+            self.ready[i].record(self.copy_stream)
+        self.head += 1
+
+    def run(self):
+        assert self.tail < self.head, "feed() a batch first"
+        i = self.tail % 2
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self.ready[i])
+        self.g.load(self.stage[i])          # device-to-device, ~100 MB: tens of microseconds
+        self.consumed[i].record(cur)
+        self.tail += 1
+        return self.g()                      # static loss tensor; float() it after feeding the next batch
+
+
 def synthetic_inputs(opt, device=None, seed=1234, pin=False):
     """Synthetic 3-frame triplets of the named HxW: U[0,1) images, KITTI-normalised K, pinv(K)."""
     import numpy as np
