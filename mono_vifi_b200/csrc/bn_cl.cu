@@ -10,6 +10,7 @@
 // (grad_y, y, x) twice and writes grad_x [+ grad_identity].  Per-channel sums are accumulated per CTA, written to a
 // workspace and added in a fixed order by a small finalize kernel (double precision): bitwise deterministic.
 #include "bn_cl.cuh"
+#include "pdl.cuh"
 
 namespace mvf {
 namespace {
@@ -22,6 +23,7 @@ __global__ void __launch_bounds__(NT) bn_partial_kernel(const float4* __restrict
                                                         const float4* __restrict__ y, const float* __restrict__ mean,
                                                         const float* __restrict__ invstd, float* __restrict__ partial, long long P,
                                                         int C4, int relu) {
+    pdl_sync();
     extern __shared__ float4 red[];  // [rows][C4] x 2
     const int rows = NT / C4 > 0 ? NT / C4 : 1;  // threads are (row, channel group); C4 <= NT is checked by the host
     const int c = threadIdx.x % C4, r = threadIdx.x / C4;
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(NT) bn_partial_kernel(const float4* __restrict
 __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int nblocks, int C, long long P, float eps, float momentum,
                                        float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
                                        float* __restrict__ running_var) {
+    pdl_sync();
     // one warp per channel: lane l adds blocks l, l+32, ...; a fixed shuffle tree combines the lanes
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
@@ -112,6 +115,7 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int nb
 // backward: d_beta = sum g, d_gamma = sum g * xhat
 __global__ void bn_finalize_bwd_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta) {
+    pdl_sync();
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
     double s = 0.0, ss = 0.0;
@@ -132,6 +136,7 @@ __global__ void bn_finalize_bwd_kernel(const float* __restrict__ partial, int nb
 __global__ void bn_apply_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ identity, float4* __restrict__ y,
                                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, long long total4, int C4, int relu) {
+    pdl_sync();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C4);
         const float4 m = *reinterpret_cast<const float4*>(mean + 4 * c), is = *reinterpret_cast<const float4*>(invstd + 4 * c);
@@ -153,6 +158,7 @@ __global__ void bn_apply_bwd_kernel(const float4* __restrict__ x, const float4* 
                                     float4* __restrict__ gx, float4* __restrict__ gid, const float* __restrict__ mean,
                                     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ dgamma,
                                     const float* __restrict__ dbeta, long long total4, int C4, float inv_P, int relu) {
+    pdl_sync();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C4);
         const float4 m = *reinterpret_cast<const float4*>(mean + 4 * c), is = *reinterpret_cast<const float4*>(invstd + 4 * c);
@@ -195,12 +201,12 @@ cudaError_t bn_forward(const float* x, const float* identity, float* y, const fl
                        float momentum, int relu, cudaStream_t st) {
     const int C4 = C / 4, nb = partial_blocks(P, C4);
     const int rows = NT / C4 > 0 ? NT / C4 : 1;
-    bn_partial_kernel<false><<<nb, NT, 2 * rows * C4 * sizeof(float4), st>>>((const float4*)x, nullptr, nullptr, nullptr, nullptr,
+    launch_pdl(bn_partial_kernel<false>, dim3((unsigned)(nb)), dim3(NT), (size_t)(2 * rows * C4 * sizeof(float4)), st, (const float4*)x, nullptr, nullptr, nullptr, nullptr,
                                                                             workspace, P, C4, 0);
-    bn_finalize_fwd_kernel<<<(C + 3) / 4, 128, 0, st>>>(workspace, nb, C, P, eps, momentum, save_mean, save_invstd, running_mean,
+    launch_pdl(bn_finalize_fwd_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), (size_t)(0), st, workspace, nb, C, P, eps, momentum, save_mean, save_invstd, running_mean,
                                                           running_var);
     const long long total4 = P * C4;
-    bn_apply_fwd_kernel<<<apply_blocks(total4), NT, 0, st>>>((const float4*)x, (const float4*)identity, (float4*)y, save_mean,
+    launch_pdl(bn_apply_fwd_kernel, dim3((unsigned)(apply_blocks(total4))), dim3(NT), (size_t)(0), st, (const float4*)x, (const float4*)identity, (float4*)y, save_mean,
                                                            save_invstd, gamma, beta, total4, C4, relu);
     return cudaGetLastError();
 }
@@ -210,11 +216,11 @@ cudaError_t bn_backward(const float* x, const float* gy, const float* y, const f
                         long long P, int C, int relu, cudaStream_t st) {
     const int C4 = C / 4, nb = partial_blocks(P, C4);
     const int rows = NT / C4 > 0 ? NT / C4 : 1;
-    bn_partial_kernel<true><<<nb, NT, 2 * rows * C4 * sizeof(float4), st>>>((const float4*)x, (const float4*)gy, (const float4*)y,
+    launch_pdl(bn_partial_kernel<true>, dim3((unsigned)(nb)), dim3(NT), (size_t)(2 * rows * C4 * sizeof(float4)), st, (const float4*)x, (const float4*)gy, (const float4*)y,
                                                                            save_mean, save_invstd, workspace, P, C4, relu);
-    bn_finalize_bwd_kernel<<<(C + 3) / 4, 128, 0, st>>>(workspace, nb, C, dgamma, dbeta);
+    launch_pdl(bn_finalize_bwd_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), (size_t)(0), st, workspace, nb, C, dgamma, dbeta);
     const long long total4 = P * C4;
-    bn_apply_bwd_kernel<<<apply_blocks(total4), NT, 0, st>>>((const float4*)x, (const float4*)gy, (const float4*)y, (float4*)gx,
+    launch_pdl(bn_apply_bwd_kernel, dim3((unsigned)(apply_blocks(total4))), dim3(NT), (size_t)(0), st, (const float4*)x, (const float4*)gy, (const float4*)y, (float4*)gx,
                                                            (float4*)gidentity, save_mean, save_invstd, gamma, dgamma, dbeta, total4,
                                                            C4, (float)(1.0 / (double)P), relu);
     return cudaGetLastError();

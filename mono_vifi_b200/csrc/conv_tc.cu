@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <mutex>
 
+#include "pdl.cuh"
 #include "tc_common.cuh"
 
 namespace mvf {
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
+    pdl_sync();  // prologue done: wait for the producer of our inputs, let the next kernel start its own prologue
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -266,6 +268,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
+    pdl_sync();  // prologue done: wait for the producer of our inputs, let the next kernel start its own prologue
 
     if (warp == 0) {
         // ===== TMA producer (one lane) =====
@@ -447,6 +450,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
 // dgrad: Wp[tap][cb][ci][kk] = w[cb*32+kk][ci][KH-1-kh][KW-1-kw]            (N = Cin,  K = Cout)
 __global__ void pack_filters_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int KH, int KW,
                                     int dgrad) {
+    pdl_sync();
     const int N = dgrad ? Cin : Cout, K = dgrad ? Cout : Cin;
     const int ncb = (K + BLOCK_K - 1) / BLOCK_K;
     const long long total = (long long)KH * KW * ncb * N * BLOCK_K;
@@ -500,8 +504,7 @@ cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const ConvA
         attr_set = true;
     }
     dim3 grid(B * a.tiles_x * a.tiles_y, (a.Cout + N_TILE - 1) / N_TILE);
-    conv_igemm_kernel<N_TILE><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(mapA, mapB, a);
-    return cudaGetLastError();
+    return launch_pdl(conv_igemm_kernel<N_TILE>, grid, dim3(NTHREADS), C::SMEM_BYTES, st, mapA, mapB, a);
 }
 
 template <int N_TILE, int MT>
@@ -523,8 +526,7 @@ cudaError_t launch_patch(const CUtensorMap& mapA, const CUtensorMap& mapB, const
         if (n_sm <= 0) n_sm = 148;
     }
     const int grid = a.n_tiles < n_sm ? a.n_tiles : n_sm;
-    conv_patch_kernel<N_TILE, MT, NB><<<grid, NTHREADS, smem, st>>>(mapA, mapB, mapY, a);
-    return cudaGetLastError();
+    return launch_pdl(conv_patch_kernel<N_TILE, MT, NB>, dim3(grid), dim3(NTHREADS), (size_t)smem, st, mapA, mapB, mapY, a);
 }
 
 }  // namespace
@@ -537,7 +539,7 @@ cudaError_t pack_filters(const float* w, float* out, int Cout, int Cin, int KH, 
     const size_t total = packed_filter_floats(dgrad ? Cin : Cout, dgrad ? Cout : Cin, KH, KW);
     const int threads = 256;
     const int blocks = (int)((total + threads - 1) / threads < 1184 ? (total + threads - 1) / threads : 1184);
-    pack_filters_kernel<<<blocks, threads, 0, st>>>(w, out, Cout, Cin, KH, KW, dgrad);
+    launch_pdl(pack_filters_kernel, dim3(blocks), dim3(threads), 0, st, w, out, Cout, Cin, KH, KW, dgrad);
     return cudaGetLastError();
 }
 

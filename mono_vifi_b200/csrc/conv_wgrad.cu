@@ -14,6 +14,7 @@
 #include <mutex>
 
 #include "conv_tc.cuh"
+#include "pdl.cuh"
 #include "tc_common.cuh"
 
 namespace mvf {
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
+    pdl_sync();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
 // dw[co][ci][tap] = sum over splits (fixed order) of partial[split][tap][co][ci]; one thread = 4 consecutive cins
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin, int taps,
                                     int ksplit, int cout_pad, int cin_pad) {
+    pdl_sync();
     const int cin4 = (Cin + 3) / 4;
     const long long total = (long long)Cout * taps * cin4;
     const size_t split_stride = (size_t)taps * cout_pad * cin_pad;
@@ -209,6 +212,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 // adds splits l, l+32, ... and a fixed shuffle tree combines the lanes -- still one summation order, so deterministic
 __global__ void wgrad_reduce_warp_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin, int taps,
                                          int ksplit, int cout_pad, int cin_pad) {
+    pdl_sync();
     const int cin4 = (Cin + 3) / 4;
     const long long total = (long long)Cout * taps * cin4;
     const size_t split_stride = (size_t)taps * cout_pad * cin_pad;
@@ -406,18 +410,18 @@ cudaError_t conv_wgrad(const WgradDesc& d, const float* x, const float* gy, floa
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_wgrad_kernel<<<grid, NTHREADS, smem, st>>>(mapG, mapX, a);
-    e = cudaGetLastError();
+    e = launch_pdl(conv_wgrad_kernel, grid, dim3(NTHREADS), (size_t)smem, st, mapG, mapX, a);
     if (e != cudaSuccess) return e;
     const long long total = (long long)d.Cout * taps * ((d.Cin + 3) / 4);
     const int threads = 256;
     if (pl.ksplit >= 16) {
         const long long nb = (total + 7) / 8;  // 8 warps per block, one warp per output group
-        wgrad_reduce_warp_kernel<<<(int)(nb < 148 * 8 ? nb : 148 * 8), threads, 0, st>>>(workspace, dw, d.Cout, d.Cin, taps, pl.ksplit,
-                                                                                        pl.cout_pad, pl.cin_pad);
+        return launch_pdl(wgrad_reduce_warp_kernel, dim3((unsigned)(nb < 148 * 8 ? nb : 148 * 8)), dim3(threads), 0, st,
+                          (const float*)workspace, dw, d.Cout, d.Cin, taps, pl.ksplit, pl.cout_pad, pl.cin_pad);
     } else {
         const int blocks = (int)((total + threads - 1) / threads < 1184 ? (total + threads - 1) / threads : 1184);
-        wgrad_reduce_kernel<<<blocks, threads, 0, st>>>(workspace, dw, d.Cout, d.Cin, taps, pl.ksplit, pl.cout_pad, pl.cin_pad);
+        return launch_pdl(wgrad_reduce_kernel, dim3(blocks), dim3(threads), 0, st, (const float*)workspace, dw, d.Cout, d.Cin, taps,
+                          pl.ksplit, pl.cout_pad, pl.cin_pad);
     }
     return cudaGetLastError();
 }

@@ -4,6 +4,7 @@
 // fused into one read of the sources and one write of the padded tensor; the backward is the exact adjoint (gather form).
 // All tensors are NCHW-shaped, channels-last in memory and dense: element (b,c,y,x) at ((b*H + y)*W + x)*C + c.
 #include "ops_cl.cuh"
+#include "pdl.cuh"
 
 namespace mvf {
 namespace {
@@ -16,6 +17,7 @@ __device__ __forceinline__ int reflect1i(int i, int n) {  // index map of Reflec
 // one thread = one float4 (4 channels) of one padded output pixel
 __global__ void upcat_pad_fwd_kernel(const float4* __restrict__ a, const float4* __restrict__ skip, float4* __restrict__ y, int B,
                                      int Ca4, int Cs4, int H, int W, int up) {
+    pdl_sync();
     const int C4 = Ca4 + Cs4, Hp = H + 2, Wp = W + 2;
     const long long total = (long long)B * Hp * Wp * C4;
     const int Ha = up ? H / 2 : H, Wa = up ? W / 2 : W;
@@ -60,6 +62,7 @@ __device__ __forceinline__ float4 pad_adjoint(const float4* __restrict__ gy, lon
 // H == 3 or W == 3 would need three terms (both folds hit the middle pixel); the host rejects those sizes.
 __global__ void upcat_pad_bwd_a_kernel(const float4* __restrict__ gy, float4* __restrict__ ga, int B, int Ca4, int Cs4, int H, int W,
                                        int up) {
+    pdl_sync();
     const int C4 = Ca4 + Cs4, Hp = H + 2, Wp = W + 2;
     const int Ha = up ? H / 2 : H, Wa = up ? W / 2 : W;
     const long long total = (long long)B * Ha * Wa * Ca4;
@@ -82,6 +85,7 @@ __global__ void upcat_pad_bwd_a_kernel(const float4* __restrict__ gy, float4* __
 }
 
 __global__ void upcat_pad_bwd_skip_kernel(const float4* __restrict__ gy, float4* __restrict__ gs, int B, int Ca4, int Cs4, int H, int W) {
+    pdl_sync();
     const int C4 = Ca4 + Cs4, Hp = H + 2, Wp = W + 2;
     const long long total = (long long)B * H * W * Cs4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -103,18 +107,18 @@ static int grid_for(long long total) {
 
 cudaError_t upcat_pad_fwd(const float* a, const float* skip, float* y, int B, int Ca, int Cs, int H, int W, int up, cudaStream_t st) {
     const long long total = (long long)B * (H + 2) * (W + 2) * ((Ca + Cs) / 4);
-    upcat_pad_fwd_kernel<<<grid_for(total), 256, 0, st>>>((const float4*)a, (const float4*)skip, (float4*)y, B, Ca / 4, Cs / 4, H, W, up);
+    launch_pdl(upcat_pad_fwd_kernel, dim3((unsigned)(grid_for(total))), dim3(256), (size_t)(0), st, (const float4*)a, (const float4*)skip, (float4*)y, B, Ca / 4, Cs / 4, H, W, up);
     return cudaGetLastError();
 }
 
 cudaError_t upcat_pad_bwd(const float* gy, float* ga, float* gskip, int B, int Ca, int Cs, int H, int W, int up, cudaStream_t st) {
     if (ga) {
         const long long total = (long long)B * (up ? H / 2 : H) * (up ? W / 2 : W) * (Ca / 4);
-        upcat_pad_bwd_a_kernel<<<grid_for(total), 256, 0, st>>>((const float4*)gy, (float4*)ga, B, Ca / 4, Cs / 4, H, W, up);
+        launch_pdl(upcat_pad_bwd_a_kernel, dim3((unsigned)(grid_for(total))), dim3(256), (size_t)(0), st, (const float4*)gy, (float4*)ga, B, Ca / 4, Cs / 4, H, W, up);
     }
     if (gskip && Cs > 0) {
         const long long total = (long long)B * H * W * (Cs / 4);
-        upcat_pad_bwd_skip_kernel<<<grid_for(total), 256, 0, st>>>((const float4*)gy, (float4*)gskip, B, Ca / 4, Cs / 4, H, W);
+        launch_pdl(upcat_pad_bwd_skip_kernel, dim3((unsigned)(grid_for(total))), dim3(256), (size_t)(0), st, (const float4*)gy, (float4*)gskip, B, Ca / 4, Cs / 4, H, W);
     }
     return cudaGetLastError();
 }
@@ -130,6 +134,7 @@ namespace {
 
 __global__ void maxpool3s2_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, uchar4* __restrict__ idx, int B, int C4,
                                       int H, int W, int Ho, int Wo) {
+    pdl_sync();
     const long long total = (long long)B * Ho * Wo * C4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C4);
@@ -162,6 +167,7 @@ __global__ void maxpool3s2_fwd_kernel(const float4* __restrict__ x, float4* __re
 
 __global__ void maxpool3s2_bwd_kernel(const float4* __restrict__ gy, const uchar4* __restrict__ idx, float4* __restrict__ gx, int B,
                                       int C4, int H, int W, int Ho, int Wo) {
+    pdl_sync();
     const long long total = (long long)B * H * W * C4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C4);
@@ -198,14 +204,14 @@ __global__ void maxpool3s2_bwd_kernel(const float4* __restrict__ gy, const uchar
 cudaError_t maxpool3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int C, int H, int W, cudaStream_t st) {
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const long long total = (long long)B * Ho * Wo * (C / 4);
-    maxpool3s2_fwd_kernel<<<grid_for(total), 256, 0, st>>>((const float4*)x, (float4*)y, (uchar4*)idx, B, C / 4, H, W, Ho, Wo);
+    launch_pdl(maxpool3s2_fwd_kernel, dim3((unsigned)(grid_for(total))), dim3(256), (size_t)(0), st, (const float4*)x, (float4*)y, (uchar4*)idx, B, C / 4, H, W, Ho, Wo);
     return cudaGetLastError();
 }
 
 cudaError_t maxpool3s2_bwd(const float* gy, const unsigned char* idx, float* gx, int B, int C, int H, int W, cudaStream_t st) {
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const long long total = (long long)B * H * W * (C / 4);
-    maxpool3s2_bwd_kernel<<<grid_for(total), 256, 0, st>>>((const float4*)gy, (const uchar4*)idx, (float4*)gx, B, C / 4, H, W, Ho, Wo);
+    launch_pdl(maxpool3s2_bwd_kernel, dim3((unsigned)(grid_for(total))), dim3(256), (size_t)(0), st, (const float4*)gy, (const uchar4*)idx, (float4*)gx, B, C / 4, H, W, Ho, Wo);
     return cudaGetLastError();
 }
 
