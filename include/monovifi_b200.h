@@ -175,17 +175,26 @@ int mvf_maxpool3s2_bwd(const float* grad_y, const unsigned char* idx, float* gra
 /* ---- fused training-mode BatchNorm2d (+ residual add) + ReLU on dense channels-last tensors [P pixels][C] -----------
  * The bn -> (+= identity) -> relu tail of torchvision's BasicBlock / Bottleneck (networks/monodepth2.py:16-31,
  * networks/posenet.py:10-52, hrnet_encoder.py:58-139).  fwd: batch statistics (biased variance for the normalisation),
- * running statistics updated as nn.BatchNorm2d does (momentum, unbiased variance; pass NULL to skip), save_mean /
+ * running statistics updated as nn.BatchNorm2d does (momentum, unbiased variance, the int64 num_batches_tracked counter
+ * incremented on the device; pass NULL to skip), save_mean /
  * save_invstd [C] kept for the backward.  bwd: grad_x, grad_gamma, grad_beta and (optional) grad_identity = masked grad_y.
  * identity / y may be NULL (no residual / relu = 0).  workspace: mvf_bn_workspace_floats(P, C) floats of scratch; the
  * per-CTA partial sums are added in a fixed order (bitwise reproducible).  C % 4 == 0, C <= 1024. */
 size_t mvf_bn_workspace_floats(long long P, int C);
 int mvf_bn_relu_fwd(const float* x, const float* identity, float* y, const float* gamma, const float* beta, float* running_mean,
-                    float* running_var, float* save_mean, float* save_invstd, float* workspace, size_t workspace_floats, long long P,
-                    int C, float eps, float momentum, int relu, void* stream);
+                    float* running_var, long long* num_batches_tracked, float* save_mean, float* save_invstd, float* workspace,
+                    size_t workspace_floats, long long P, int C, float eps, float momentum, int relu, void* stream);
 int mvf_bn_relu_bwd(const float* x, const float* grad_y, const float* y, const float* gamma, const float* save_mean,
                     const float* save_invstd, float* grad_x, float* grad_identity, float* grad_gamma, float* grad_beta,
                     float* workspace, size_t workspace_floats, long long P, int C, int relu, void* stream);
+
+/* Backward of the activation fused into a convolution's epilogue plus the bias gradient, one pass over dense
+ * channels-last [P pixels][C]: grad_pre = grad_y * act'(y) (act 0 none, 1 relu, 2 elu(alpha=1), from the saved OUTPUT y)
+ * and grad_bias[c] = sum_p grad_pre[p][c] (fixed-order, reproducible).  Replaces elu_backward / threshold_backward +
+ * `grad.sum((0,2,3))` behind layers.py:68-117 (ConvBlock / Conv3x3 with bias).  grad_bias may be NULL (activation only);
+ * grad_pre may be NULL when act == 0 (bias gradient only).  workspace: mvf_bn_workspace_floats(P, C). */
+int mvf_act_bwd_bias(const float* grad_y, const float* y, float* grad_pre, float* grad_bias, float* workspace, size_t workspace_floats,
+                     long long P, int C, int act, void* stream);
 
 /* ---- fused torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.step over ONE flat fp32 arena (train.py:661-666) --------
  * params / grads / exp_avg / exp_avg_sq: n floats each, 16-byte aligned.  state[2] (device): {step count, last gradient
@@ -197,6 +206,13 @@ size_t mvf_adamw_workspace_bytes(void);
 int mvf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,
                    void* workspace, size_t workspace_bytes, float lr, float beta1, float beta2, float eps, float weight_decay,
                    float max_norm, void* stream);
+
+/* Gathers the per-parameter gradient tensors autograd produced into the flat arena mvf_adamw_step reads (and the one
+ * data-parallel all-reduce runs on): grads[i] (device pointer, host array; NULL = no gradient this step, slice zeroed)
+ * -> arena[offsets[i] .. offsets[i] + sizes[i]).  Offsets must be multiples of 4 floats.  One launch per 128 tensors;
+ * replaces the ~200 `param.grad += g` launches of torch's AccumulateGrad + DDP's bucket copies (train.py:205-208). */
+int mvf_gather_grads(float* arena, const void* const* grads, const long long* offsets, const long long* sizes, int n_tensors,
+                     void* stream);
 
 /* device self-test: q_sequence[i] = the kernels' shared-reciprocal division of a[i] by b[i], q_ieee[i] = the
  * IEEE quotient (div.rn.f32); the two must be bit-identical for operands in the normal range. */

@@ -57,10 +57,13 @@ SIGNATURES = {
     "mvf_maxpool3s2_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mvf_maxpool3s2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mvf_bn_workspace_floats": (_sz, [ctypes.c_longlong, _i]),
-    "mvf_bn_relu_fwd": (_i, [_vp] * 10 + [_sz, ctypes.c_longlong, _i, _f, _f, _i, _vp]),
+    "mvf_bn_relu_fwd": (_i, [_vp] * 11 + [_sz, ctypes.c_longlong, _i, _f, _f, _i, _vp]),
     "mvf_bn_relu_bwd": (_i, [_vp] * 11 + [_sz, ctypes.c_longlong, _i, _i, _vp]),
+    "mvf_act_bwd_bias": (_i, [_vp] * 5 + [_sz, ctypes.c_longlong, _i, _i, _vp]),
     "mvf_adamw_workspace_bytes": (_sz, []),
     "mvf_adamw_step": (_i, [_vp, _vp, _vp, _vp, ctypes.c_longlong, _vp, _vp, _sz, _f, _f, _f, _f, _f, _f, _vp]),
+    "mvf_gather_grads": (_i, [_vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_longlong),
+                              ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, _vp]),
     "mvf_selftest_umma": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "mvf_selftest_umma_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mvf_conv2d_debug_buffer": (None, [_vp]),

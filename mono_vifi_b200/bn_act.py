@@ -37,7 +37,7 @@ def _dense_cl(t):
 
 class _BNAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, identity, weight, bias, running_mean, running_var, eps, momentum, relu):
+    def forward(ctx, x, identity, weight, bias, running_mean, running_var, nbt, eps, momentum, relu):
         x = _dense_cl(x)
         B, C, H, W = x.shape
         P = B * H * W
@@ -52,7 +52,8 @@ class _BNAct(torch.autograd.Function):
         launches["bn_fwd"] += 1
         _lib.check(L.mvf_bn_relu_fwd(x.data_ptr(), None if identity is None else identity.data_ptr(), y.data_ptr(), weight.data_ptr(),
                                      bias.data_ptr(), None if running_mean is None else running_mean.data_ptr(),
-                                     None if running_var is None else running_var.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                     None if running_var is None else running_var.data_ptr(),
+                                     None if nbt is None else nbt.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
                                      ws.data_ptr(), ws.numel(), P, C, eps, momentum, 1 if relu else 0, st), "mvf_bn_relu_fwd")
         ctx.save_for_backward(x, y, weight, mean, invstd)
         ctx.relu, ctx.has_identity = relu, identity is not None
@@ -76,7 +77,7 @@ class _BNAct(torch.autograd.Function):
         _lib.check(L.mvf_bn_relu_bwd(x.data_ptr(), gy.data_ptr(), y.data_ptr(), weight.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
                                      gx.data_ptr(), None if gid is None else gid.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
                                      ws.data_ptr(), ws.numel(), P, C, 1 if ctx.relu else 0, st), "mvf_bn_relu_bwd")
-        return gx, gid, dgamma, dbeta, None, None, None, None, None
+        return gx, gid, dgamma, dbeta, None, None, None, None, None, None
 
 
 def usable(bn, x):
@@ -87,10 +88,11 @@ def usable(bn, x):
 def bn_act(bn, x, identity=None, relu=True):
     """relu(bn(x) + identity) with nn.BatchNorm2d `bn` (its parameters / buffers are used and updated in place)."""
     if usable(bn, x):
-        if bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
-        rm, rv = (bn.running_mean, bn.running_var) if bn.track_running_stats else (None, None)
-        return _BNAct.apply(x, identity, bn.weight, bn.bias, rm, rv, float(bn.eps), float(bn.momentum), bool(relu))
+        rm, rv, nbt = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if bn.track_running_stats else (None, None, None)
+        if nbt is not None and nbt.dtype != torch.int64:
+            nbt.add_(1)
+            nbt = None
+        return _BNAct.apply(x, identity, bn.weight, bn.bias, rm, rv, nbt, float(bn.eps), float(bn.momentum), bool(relu))
     y = bn(x)
     if identity is not None:
         y = y + identity

@@ -115,6 +115,34 @@ def conv_forward_raw(x, w_packed, bias, Cout, KH, KW, pad, stride=1, act=0, out=
 ACT = {None: 0, "none": 0, "relu": 1, "elu": 2}
 
 
+def _dense_cl(t):
+    B, C, H, W = t.shape
+    return t.dtype == torch.float32 and tuple(t.stride()) == (H * W * C, 1, W * C, C) and t.data_ptr() % 16 == 0
+
+
+_bias_ws = {}
+
+
+def act_bwd_bias(gy, y, act, want_bias):
+    """(gy * act'(y), sum over pixels of that) in one pass (C ABI: mvf_act_bwd_bias); dense channels-last inputs"""
+    B, C, H, W = gy.shape
+    P = B * H * W
+    L = _lib.lib()
+    gpre = torch.empty(B, H, W, C, device=gy.device, dtype=torch.float32).permute(0, 3, 1, 2) if act else None
+    gb = torch.empty(C, device=gy.device, dtype=torch.float32) if want_bias else None
+    ws = None
+    if want_bias:
+        n = L.mvf_bn_workspace_floats(P, C)
+        key = (gy.device.index, _stream(gy))
+        ws = _bias_ws.get(key)
+        if ws is None or ws.numel() < n:
+            ws = _bias_ws[key] = torch.empty(max(n, 1 << 18), device=gy.device, dtype=torch.float32)
+    _lib.check(L.mvf_act_bwd_bias(gy.data_ptr(), None if y is None else y.data_ptr(), None if gpre is None else gpre.data_ptr(),
+                                  None if gb is None else gb.data_ptr(), None if ws is None else ws.data_ptr(),
+                                  0 if ws is None else ws.numel(), P, C, act, _stream(gy)), "mvf_act_bwd_bias")
+    return (gpre if act else gy), gb
+
+
 class _Conv2dTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, pad, stride, act):
@@ -135,10 +163,15 @@ class _Conv2dTC(torch.autograd.Function):
         Cout, Cin, KH, KW = weight.shape
         pad, stride = ctx.pad, ctx.stride
         gx = gw = gb = None
-        if ctx.act == 1:
-            gy = torch.ops.aten.threshold_backward(gy, ctx.saved_tensors[2], 0.0)
+        want_gb = ctx.has_bias and ctx.needs_input_grad[2]
+        yact = ctx.saved_tensors[2] if ctx.act else None
+        if (ctx.act or want_gb) and _dense_cl(gy) and (yact is None or _dense_cl(yact)) and Cout % 4 == 0 and Cout <= 1024:
+            gy, gb = act_bwd_bias(gy, yact, ctx.act, want_gb)   # one pass: activation backward + bias gradient
+            want_gb = False
+        elif ctx.act == 1:
+            gy = torch.ops.aten.threshold_backward(gy, yact, 0.0)
         elif ctx.act == 2:  # d elu / d pre-activation from the saved OUTPUT: 1 where y > 0, y + 1 elsewhere
-            gy = torch.ops.aten.elu_backward(gy, 1.0, 1.0, 1.0, True, ctx.saved_tensors[2])
+            gy = torch.ops.aten.elu_backward(gy, 1.0, 1.0, 1.0, True, yact)
         gy = _as_input(gy)
         if ctx.needs_input_grad[0]:
             if _pair(stride) == (1, 1) and pad <= KH - 1 and pad <= KW - 1:
@@ -159,7 +192,7 @@ class _Conv2dTC(torch.autograd.Function):
                 gx = input_grad_library(x, gy, weight, pad, stride)
         if ctx.needs_input_grad[1]:
             gw = weight_grad(x, gy, weight.shape, pad, stride)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if want_gb:
             gb = gy.sum((0, 2, 3))
         return gx, gw, gb, None, None, None
 

@@ -323,12 +323,12 @@ int mvf_maxpool3s2_bwd(const float* grad_y, const unsigned char* idx, float* gra
 /* ---- fused BatchNorm2d (training) + residual add + ReLU, channels-last ------------------------------------------- */
 size_t mvf_bn_workspace_floats(long long P, int C) { return (P > 0 && C > 0 && C % 4 == 0 && C <= 1024) ? mvf::bn_workspace_floats(P, C) : 0; }
 int mvf_bn_relu_fwd(const float* x, const float* identity, float* y, const float* gamma, const float* beta, float* running_mean,
-                    float* running_var, float* save_mean, float* save_invstd, float* workspace, size_t workspace_floats, long long P,
-                    int C, float eps, float momentum, int relu, void* stream) {
+                    float* running_var, long long* num_batches_tracked, float* save_mean, float* save_invstd, float* workspace,
+                    size_t workspace_floats, long long P, int C, float eps, float momentum, int relu, void* stream) {
     if (!x || !y || !gamma || !beta || !save_mean || !save_invstd || !workspace || P <= 0 || C <= 0 || (C % 4) || C > 1024)
         return fail(MVF_ERR_INVALID, "mvf_bn_relu_fwd: bad argument (C % 4 == 0, C <= 1024)");
     if (workspace_floats < mvf::bn_workspace_floats(P, C)) return fail(MVF_ERR_WORKSPACE, "mvf_bn_relu_fwd: workspace too small");
-    MVF_RUN("mvf_bn_relu_fwd", mvf::bn_forward(x, identity, y, gamma, beta, running_mean, running_var, save_mean, save_invstd, workspace,
+    MVF_RUN("mvf_bn_relu_fwd", mvf::bn_forward(x, identity, y, gamma, beta, running_mean, running_var, num_batches_tracked, save_mean, save_invstd, workspace,
                                                P, C, eps, momentum, relu, (cudaStream_t)stream));
 }
 int mvf_bn_relu_bwd(const float* x, const float* grad_y, const float* y, const float* gamma, const float* save_mean,
@@ -342,6 +342,15 @@ int mvf_bn_relu_bwd(const float* x, const float* grad_y, const float* y, const f
                                                 workspace, P, C, relu, (cudaStream_t)stream));
 }
 
+int mvf_act_bwd_bias(const float* grad_y, const float* y, float* grad_pre, float* grad_bias, float* workspace, size_t workspace_floats,
+                     long long P, int C, int act, void* stream) {
+    if (!grad_y || P <= 0 || C <= 0 || (C % 4) || C > 1024 || act < 0 || act > 2 || (act && (!y || !grad_pre)) || (!grad_pre && !grad_bias))
+        return fail(MVF_ERR_INVALID, "mvf_act_bwd_bias: bad argument (C % 4 == 0, C <= 1024, act in 0..2)");
+    if (grad_bias && (!workspace || workspace_floats < mvf::bn_workspace_floats(P, C)))
+        return fail(MVF_ERR_WORKSPACE, "mvf_act_bwd_bias: workspace too small");
+    MVF_RUN("mvf_act_bwd_bias", mvf::act_bwd_bias(grad_y, y, grad_pre, grad_bias, workspace, P, C, act, (cudaStream_t)stream));
+}
+
 /* ---- fused clip_grad_norm_ + AdamW over a flat arena -------------------------------------------------------------- */
 size_t mvf_adamw_workspace_bytes(void) { return mvf::adamw_workspace_bytes(); }
 int mvf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,
@@ -353,6 +362,15 @@ int mvf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp
         return fail(MVF_ERR_INVALID, "mvf_adamw_step: arenas must be 16-byte aligned");
     MVF_RUN("mvf_adamw_step", mvf::adamw_step(params, grads, exp_avg, exp_avg_sq, n, state, workspace, lr, beta1, beta2, eps,
                                               weight_decay, max_norm, (cudaStream_t)stream));
+}
+
+int mvf_gather_grads(float* arena, const void* const* grads, const long long* offsets, const long long* sizes, int n_tensors,
+                     void* stream) {
+    if (!arena || !grads || !offsets || !sizes || n_tensors <= 0) return fail(MVF_ERR_INVALID, "mvf_gather_grads: bad argument");
+    if (((uintptr_t)arena & 15) != 0) return fail(MVF_ERR_INVALID, "mvf_gather_grads: arena must be 16-byte aligned");
+    for (int i = 0; i < n_tensors; ++i)
+        if (offsets[i] < 0 || (offsets[i] & 3) != 0 || sizes[i] < 0) return fail(MVF_ERR_INVALID, "mvf_gather_grads: offsets must be non-negative multiples of 4");
+    MVF_RUN("mvf_gather_grads", mvf::gather_grads(arena, grads, offsets, sizes, n_tensors, (cudaStream_t)stream));
 }
 
 }  // extern "C"

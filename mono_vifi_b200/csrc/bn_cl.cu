@@ -84,8 +84,9 @@ __global__ void __launch_bounds__(NT) bn_partial_kernel(const float4* __restrict
 // forward: mean / biased variance -> (mean, invstd) saved for backward, running statistics updated as nn.BatchNorm2d does
 __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int nblocks, int C, long long P, float eps, float momentum,
                                        float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
-                                       float* __restrict__ running_var) {
+                                       float* __restrict__ running_var, long long* __restrict__ num_batches_tracked) {
     pdl_sync();
+    if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
     // one warp per channel: lane l adds blocks l, l+32, ...; a fixed shuffle tree combines the lanes
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
@@ -180,6 +181,66 @@ __global__ void bn_apply_bwd_kernel(const float4* __restrict__ x, const float4* 
     }
 }
 
+// ---- activation backward + bias gradient of a convolution output, one pass --------------------------------------
+// gpre = gy * act'(y) (act: 0 none, 1 relu, 2 elu, both from the saved OUTPUT) and partial[block][c] = this block's
+// share of sum_pixels gpre[.., c]; the finalize kernel adds the blocks in a fixed order.
+__global__ void __launch_bounds__(NT) act_bias_partial_kernel(const float4* __restrict__ gy, const float4* __restrict__ y,
+                                                              float4* __restrict__ gpre, float* __restrict__ partial, long long P,
+                                                              int C4, int act) {
+    pdl_sync();
+    extern __shared__ float4 red[];  // [rows][C4]
+    const int rows = NT / C4 > 0 ? NT / C4 : 1;
+    const int c = threadIdx.x % C4, r = threadIdx.x / C4;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows) {
+        const long long step = (long long)gridDim.x * rows;
+        for (long long p0 = (long long)blockIdx.x * rows + r; p0 < P; p0 += 4 * step) {
+            float4 g[4], o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long p = p0 + u * step;
+                const bool ok = p < P;
+                g[u] = ok ? __ldg(gy + p * C4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                o[u] = (ok && act) ? __ldg(y + p * C4 + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float4 q = g[u];
+                if (act == 1) {
+                    q.x = o[u].x > 0.f ? q.x : 0.f; q.y = o[u].y > 0.f ? q.y : 0.f; q.z = o[u].z > 0.f ? q.z : 0.f; q.w = o[u].w > 0.f ? q.w : 0.f;
+                } else if (act == 2) {
+                    q.x = o[u].x > 0.f ? q.x : q.x * (o[u].x + 1.f); q.y = o[u].y > 0.f ? q.y : q.y * (o[u].y + 1.f);
+                    q.z = o[u].z > 0.f ? q.z : q.z * (o[u].z + 1.f); q.w = o[u].w > 0.f ? q.w : q.w * (o[u].w + 1.f);
+                }
+                const long long p = p0 + u * step;
+                if (gpre && p < P) gpre[p * C4 + c] = q;
+                s0.x += q.x; s0.y += q.y; s0.z += q.z; s0.w += q.w;
+            }
+        }
+        red[r * C4 + c] = s0;
+    }
+    __syncthreads();
+    if (partial && threadIdx.x < C4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < rows; ++q) {  // fixed order
+            const float4 u = red[q * C4 + threadIdx.x];
+            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+        }
+        reinterpret_cast<float4*>(partial)[(size_t)blockIdx.x * C4 + threadIdx.x] = a;
+    }
+}
+
+__global__ void bias_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ gbias) {
+    pdl_sync();
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int b = lane; b < nblocks; b += 32) s += (double)partial[(size_t)b * C + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) gbias[c] = (float)s;
+}
+
 int partial_blocks(long long P, int C4) {
     const int rows = NT / C4 > 0 ? NT / C4 : 1;
     long long nb = (P + (long long)rows * 16 - 1) / ((long long)rows * 16);  // at least ~16 pixels per thread
@@ -197,14 +258,14 @@ int apply_blocks(long long total4) {
 size_t bn_workspace_floats(long long P, int C) { return (size_t)partial_blocks(P, C / 4) * 2 * C; }
 
 cudaError_t bn_forward(const float* x, const float* identity, float* y, const float* gamma, const float* beta, float* running_mean,
-                       float* running_var, float* save_mean, float* save_invstd, float* workspace, long long P, int C, float eps,
-                       float momentum, int relu, cudaStream_t st) {
+                       float* running_var, long long* num_batches_tracked, float* save_mean, float* save_invstd, float* workspace,
+                       long long P, int C, float eps, float momentum, int relu, cudaStream_t st) {
     const int C4 = C / 4, nb = partial_blocks(P, C4);
     const int rows = NT / C4 > 0 ? NT / C4 : 1;
     launch_pdl(bn_partial_kernel<false>, dim3((unsigned)(nb)), dim3(NT), (size_t)(2 * rows * C4 * sizeof(float4)), st, (const float4*)x, nullptr, nullptr, nullptr, nullptr,
                                                                             workspace, P, C4, 0);
     launch_pdl(bn_finalize_fwd_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), (size_t)(0), st, workspace, nb, C, P, eps, momentum, save_mean, save_invstd, running_mean,
-                                                          running_var);
+               running_var, num_batches_tracked);
     const long long total4 = P * C4;
     launch_pdl(bn_apply_fwd_kernel, dim3((unsigned)(apply_blocks(total4))), dim3(NT), (size_t)(0), st, (const float4*)x, (const float4*)identity, (float4*)y, save_mean,
                                                            save_invstd, gamma, beta, total4, C4, relu);
@@ -223,6 +284,16 @@ cudaError_t bn_backward(const float* x, const float* gy, const float* y, const f
     launch_pdl(bn_apply_bwd_kernel, dim3((unsigned)(apply_blocks(total4))), dim3(NT), (size_t)(0), st, (const float4*)x, (const float4*)gy, (const float4*)y, (float4*)gx,
                                                            (float4*)gidentity, save_mean, save_invstd, gamma, dgamma, dbeta, total4,
                                                            C4, (float)(1.0 / (double)P), relu);
+    return cudaGetLastError();
+}
+
+cudaError_t act_bwd_bias(const float* gy, const float* y, float* gpre, float* gbias, float* workspace, long long P, int C, int act,
+                         cudaStream_t st) {
+    const int C4 = C / 4, nb = partial_blocks(P, C4);
+    const int rows = NT / C4 > 0 ? NT / C4 : 1;
+    launch_pdl(act_bias_partial_kernel, dim3((unsigned)nb), dim3(NT), (size_t)(rows * C4 * sizeof(float4)), st, (const float4*)gy,
+               (const float4*)y, (float4*)gpre, gbias ? workspace : nullptr, P, C4, act);
+    if (gbias) launch_pdl(bias_finalize_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), (size_t)0, st, (const float*)workspace, nb, C, gbias);
     return cudaGetLastError();
 }
 

@@ -7,6 +7,8 @@
 // HBM-bound: pass 1 reads 4 B/param, pass 2 reads 16 and writes 12 B/param.
 #include "optim.cuh"
 
+#include <stdint.h>
+
 namespace mvf {
 namespace {
 
@@ -85,7 +87,60 @@ __global__ void adamw_tick_kernel(float* state, const double* partial, int nb) {
     state[1] = (float)sqrt(ss);
 }
 
+// Multi-tensor gather: autograd leaves one gradient tensor per parameter; this copies up to GATHER_MAX of them per launch
+// into their slices of the flat arena (blockIdx.y = tensor, blockIdx.x strides over it), so the parameters' .grad can
+// stay None between steps -- autograd then adopts each gradient instead of launching one `grad += new` per parameter.
+constexpr int GATHER_MAX = 128;
+struct GatherTable {
+    const float* src[GATHER_MAX];
+    long long off[GATHER_MAX];
+    long long n[GATHER_MAX];
+};
+
+__global__ void __launch_bounds__(NT) gather_grads_kernel(const __grid_constant__ GatherTable t, float* __restrict__ G) {
+    const float* __restrict__ src = t.src[blockIdx.y];
+    float* __restrict__ dst = G + t.off[blockIdx.y];
+    const long long n = t.n[blockIdx.y];
+    if (src == nullptr) {  // parameter without a gradient this step
+        for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) dst[i] = 0.f;
+        return;
+    }
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {  // arena slices are 16-byte aligned by construction
+        const long long n4 = n / 4;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) d4[i] = __ldg(s4 + i);
+        if (blockIdx.x == 0) {
+            const long long i = n4 * 4 + threadIdx.x;
+            if (i < n) dst[i] = src[i];
+        }
+    } else {
+        for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) dst[i] = src[i];
+    }
+}
+
 }  // namespace
+
+cudaError_t gather_grads(float* G, const void* const* srcs, const long long* offsets, const long long* sizes, int n_tensors,
+                         cudaStream_t st) {
+    for (int base = 0; base < n_tensors; base += GATHER_MAX) {
+        GatherTable t;
+        const int cnt = n_tensors - base < GATHER_MAX ? n_tensors - base : GATHER_MAX;
+        long long nmax = 1;
+        for (int i = 0; i < GATHER_MAX; ++i) {
+            const bool ok = i < cnt;
+            t.src[i] = ok ? reinterpret_cast<const float*>(srcs[base + i]) : nullptr;
+            t.off[i] = ok ? offsets[base + i] : 0;
+            t.n[i] = ok ? sizes[base + i] : 0;
+            if (ok && sizes[base + i] > nmax) nmax = sizes[base + i];
+        }
+        long long bx = (nmax / 4 + NT * 8 - 1) / (NT * 8);  // ~8 float4 per thread on the largest tensor
+        if (bx < 1) bx = 1;
+        if (bx > 64) bx = 64;
+        gather_grads_kernel<<<dim3((unsigned)bx, (unsigned)cnt), NT, 0, st>>>(t, G);
+    }
+    return cudaGetLastError();
+}
 
 size_t adamw_workspace_bytes() { return NB_NORM * sizeof(double); }
 

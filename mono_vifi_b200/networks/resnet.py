@@ -9,6 +9,15 @@ from ..conv import Conv2d
 from ..decoder_ops import MaxPool3s2
 
 
+def _shortcut(downsample, x):
+    """identity branch: nothing, or the 1x1 strided conv + bn pair (bn through the fused kernels, no activation)"""
+    if downsample is None:
+        return x
+    if isinstance(downsample, nn.Sequential) and len(downsample) == 2 and isinstance(downsample[1], nn.BatchNorm2d):
+        return bn_act(downsample[1], downsample[0](x), None, relu=False)
+    return downsample(x)
+
+
 class BasicBlock(nn.Module):
     expansion = 1
 
@@ -23,7 +32,7 @@ class BasicBlock(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        identity = x if self.downsample is None else self.downsample(x)
+        identity = _shortcut(self.downsample, x)
         out = bn_act(self.bn1, self.conv1(x))                        # bn + relu in one pass
         return bn_act(self.bn2, self.conv2(out), identity)           # bn + residual add + relu in one pass
 
@@ -44,7 +53,7 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        identity = x if self.downsample is None else self.downsample(x)
+        identity = _shortcut(self.downsample, x)
         out = bn_act(self.bn1, self.conv1(x))
         out = bn_act(self.bn2, self.conv2(out))
         return bn_act(self.bn3, self.conv3(out), identity)

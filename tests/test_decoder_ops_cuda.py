@@ -110,3 +110,32 @@ def test_fused_bn_add_relu_matches_torch(case):
         pairs.append((idn.grad, ir.grad))
     for got, want in pairs:
         assert (got.double() - want).abs().max().item() <= 1e-4 * max(1e-3, want.abs().max().item())
+
+
+@pytest.mark.parametrize("case", [(2, 16, 9, 13, 2, True), (12, 64, 24, 80, 1, True), (1, 256, 6, 20, 0, True), (3, 32, 7, 5, 2, False),
+                                  (2, 1024, 3, 4, 1, True)])
+def test_act_backward_and_bias_gradient_match_torch(case):
+    """mvf_act_bwd_bias vs aten elu_backward / threshold_backward + sum((0,2,3)) (the backward of layers.py:68-117)"""
+    import torch
+    from mono_vifi_b200 import conv_tc
+    B, C, H, W, act, want_bias = case
+    g = torch.Generator(device="cuda").manual_seed(11)
+    gy = torch.randn(B, C, H, W, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    y = torch.randn(B, C, H, W, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    if act == 2:
+        y = torch.where(y > 0, y, torch.expm1(y))
+    elif act == 1:
+        y = torch.relu(y)
+    gpre, gb = conv_tc.act_bwd_bias(gy, y if act else None, act, want_bias)
+    if act == 1:
+        ref = torch.ops.aten.threshold_backward(gy, y, 0.0)
+    elif act == 2:
+        ref = torch.ops.aten.elu_backward(gy, 1.0, 1.0, 1.0, True, y)
+    else:
+        ref = gy
+    assert torch.equal(gpre, ref) or torch.allclose(gpre, ref, rtol=1e-6, atol=1e-7)
+    if want_bias:
+        refb = ref.double().sum((0, 2, 3))
+        assert torch.allclose(gb.double(), refb, rtol=1e-5, atol=1e-5 * float(ref.abs().sum((0, 2, 3)).max()))
+    else:
+        assert gb is None
