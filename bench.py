@@ -197,7 +197,7 @@ class ClockSampler:
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from mono_vifi_b200 import _lib, conv, conv_tc, ddp, fused, trainer as TR
+    from mono_vifi_b200 import _lib, bn_act, conv, conv_tc, ddp, fused, trainer as TR
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (our arm) needs a CUDA device: there is no CPU fallback")
@@ -228,13 +228,15 @@ def run_ours(args):
     for i in range(max(1, args.warmup - 2)):
         step(resident[i % 2])
     fused.timing, conv_tc.timing = [], []
-    l0, c0 = dict(fused.launches), dict(conv_tc.launches)
+    l0, c0, b0 = dict(fused.launches), dict(conv_tc.launches), dict(bn_act.launches)
     for k in conv.stats:
         conv.stats[k] = 0
     n_eager = 2
+    side, step.side = step.side, None  # per-kernel event timing wants the kernels alone on the GPU: no concurrent pose branch
     for i in range(n_eager):
         step(resident[i % 2])
     torch.cuda.synchronize()
+    step.side = side
     kt = {"f1_fwd": [], "f1_bwd": []}
     for tag, a, b in fused.timing:
         kt[tag].append(a.elapsed_time(b))
@@ -247,7 +249,11 @@ def run_ours(args):
     fused.timing = conv_tc.timing = None
     conv_launches = {k: (conv_tc.launches[k] - c0[k]) // n_eager for k in c0}
     conv_calls = {k: v // n_eager for k, v in conv.stats.items()}
-    launches_per_step = sum(fused.launches[k] - l0[k] for k in l0) // n_eager + sum(conv_launches.values())
+    bn_calls = {k: (bn_act.launches[k] - b0[k]) // n_eager for k in b0}
+    # F1 + convolution kernels + 3 kernels per fused BN call + (sum of squares, AdamW, tick, gradient gather) of the optimiser;
+    # the decoder's upcat / max-pool / activation-backward kernels are not counted (under-claim)
+    launches_per_step = (sum(fused.launches[k] - l0[k] for k in l0) // n_eager + sum(conv_launches.values()) + 3 * sum(bn_calls.values()) +
+                         (0 if args.torch_optimizer else 5))
     # ---- the step as a CUDA graph (one launch per step) ---------------------------------------------------------
     graph_note = "eager launches (--no-graph)"
     run = step
@@ -343,10 +349,10 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32 (tf32 tensor-core convolutions, as torch's cuDNN default)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": args.batch, "global_batch": args.batch * world,
                        "height": args.height, "width": args.width, "parallelism": "dp%d" % world,
-                       "launch": graph_note,
+                       "launch": graph_note, "streams": "pose branch on a second stream, concurrent with the depth branch" if step.side is not None else "one stream",
                        "optimizer": "torch clip_grad_norm_ + AdamW" if args.torch_optimizer else "fused clip + AdamW over flat arenas (mvf_adamw_step)",
                        "conv_backend": conv.get_backend(), "conv_calls_per_step": conv_calls,
-                       "conv_kernel_launches_per_step": conv_launches,
+                       "conv_kernel_launches_per_step": conv_launches, "bn_calls_per_step": bn_calls,
                        "l2": "working set (activations, several GB) is far larger than the 126 MB L2; inputs rotate between two batches"},
             "e2e": {"value": args.batch * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},

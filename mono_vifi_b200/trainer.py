@@ -6,6 +6,8 @@ backward, gradient clipping and AdamW (train.py:659-666) -- on top of the drop-i
 photometric-loss kernel.  Data-parallel training shards the batch across ranks; gradients are averaged with ONE
 NCCL all-reduce over a flat fp32 arena (mono_vifi_b200/ddp.py) instead of the reference's five DDP wrappers.
 """
+import os
+
 import torch
 
 from . import layers as L
@@ -92,13 +94,47 @@ def loss_group(opt, disp, img_tgt, T0, T1, img_src0, img_src1, K, inv_K, mask_re
                                   opt.disable_automasking)
 
 
-def single_frame_losses(models, inputs, opt):
-    """The single-frame slice of process_batch: train.py:728-729 (poses), 736 + 739 (depth), 747-750 (loss)."""
+class _Fork:
+    """`with _Fork(side):` runs its body on the stream `side`, ordered after everything already queued on the current
+    stream; join() makes the current stream wait for it and tells the allocator that the given tensors (allocated on
+    `side`) are now used on the current stream.  With side None the body runs inline."""
+
+    def __init__(self, side):
+        self.side = side
+        self.cur = torch.cuda.current_stream(side.device) if side is not None else None
+        self.ctx = None
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(self.cur)
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self, *tensors):
+        if self.side is not None:
+            self.cur.wait_stream(self.side)
+            for t in tensors:
+                t.record_stream(self.cur)
+
+
+def single_frame_losses(models, inputs, opt, side=None):
+    """The single-frame slice of process_batch: train.py:728-729 (poses), 736 + 739 (depth), 747-750 (loss).
+    The pose branch and the depth branch are independent until the loss: with `side` (a CUDA stream) the two pose
+    passes run there while the depth network runs on the current stream, so their short kernels (1-3 tiles per SM, many
+    with fewer CTAs than SMs) fill each other's idle SMs; autograd replays the same split in the backward."""
     img_n1, img_0, img_p1 = inputs[("color", -1, 0)], inputs[("color", 0, 0)], inputs[("color", 1, 0)]
     K, inv_K = inputs[("K", 0)], inputs[("inv_K", 0)]
-    pose_n1_0, pose_0_n1 = predict_poses(models, inputs[("color_aug", -1, 0)], inputs[("color_aug", 0, 0)])
-    pose_0_p1, pose_p1_0 = predict_poses(models, inputs[("color_aug", 0, 0)], inputs[("color_aug", 1, 0)])
+    with _Fork(side) as fork:
+        pose_n1_0, pose_0_n1 = predict_poses(models, inputs[("color_aug", -1, 0)], inputs[("color_aug", 0, 0)])
+        pose_0_p1, pose_p1_0 = predict_poses(models, inputs[("color_aug", 0, 0)], inputs[("color_aug", 1, 0)])
     disp_0 = models["depth"](models["encoder"](inputs[("color_aug", 0, 0)]))[("disp", 0)]
+    fork.join(pose_0_n1, pose_0_p1)
     loss, auto_mask = loss_group(opt, disp_0, img_0, pose_0_n1, pose_0_p1, img_n1, img_p1, K, inv_K)
     return {"loss": loss, "loss_base": loss, "disp": disp_0, "auto_mask": auto_mask}
 
@@ -182,6 +218,9 @@ class TrainStep:
         # accumulator to the stream of its first use; binding them to the legacy default stream would make the step
         # impossible to record into a CUDA graph later (GraphedTrainStep).
         self.stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+        # second stream for the pose branch of the single-frame step (MVF_SIDE_STREAM=0 serialises everything)
+        self.side = (torch.cuda.Stream(device=device)
+                     if device.type == "cuda" and os.environ.get("MVF_SIDE_STREAM", "1") != "0" else None)
 
     def train(self):
         for m in self.models.values():
@@ -197,8 +236,10 @@ class TrainStep:
         if self.opt.multi_frame:
             out = multi_frame_losses(self.models, self.vfi, inputs, self.opt)
         else:
-            out = single_frame_losses(self.models, inputs, self.opt)
+            out = single_frame_losses(self.models, inputs, self.opt, side=self.side)
         out["loss"].backward()
+        if self.side is not None:  # parameter gradients of the pose branch were produced on the side stream
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
         if self.reducer is not None:
             self.reducer.allreduce_mean()
         return out
