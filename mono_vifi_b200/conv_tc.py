@@ -7,6 +7,8 @@ tells the dispatcher in conv.py which problems the kernels cover; nothing here f
 Activations are NCHW-shaped tensors in torch.channels_last memory format (the kernels' TMA boxes need channels
 contiguous); tensors arriving in another layout are converted once on entry.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -143,6 +145,18 @@ def act_bwd_bias(gy, y, act, want_bias):
     return (gpre if act else gy), gb
 
 
+wgrad_stream_enabled = os.environ.get("MVF_WGRAD_STREAM", "1") != "0"
+_companions = {}
+
+
+def _companion(cur):
+    key = (cur.device.index, cur.cuda_stream)
+    st = _companions.get(key)
+    if st is None:
+        st = _companions[key] = torch.cuda.Stream(device=cur.device)
+    return st
+
+
 class _Conv2dTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, pad, stride, act):
@@ -173,6 +187,15 @@ class _Conv2dTC(torch.autograd.Function):
         elif ctx.act == 2:  # d elu / d pre-activation from the saved OUTPUT: 1 where y > 0, y + 1 elsewhere
             gy = torch.ops.aten.elu_backward(gy, 1.0, 1.0, 1.0, True, yact)
         gy = _as_input(gy)
+        # dL/dw and dL/dx of one layer are independent: the weight gradient goes to a companion stream so that the two
+        # kernels (each 1-3 tiles per SM) share the GPU; joined before this node returns, so nothing downstream changes
+        fork = None
+        if ctx.needs_input_grad[1] and ctx.needs_input_grad[0] and wgrad_stream_enabled and timing is None and gy.is_cuda:
+            cur = torch.cuda.current_stream(gy.device)
+            fork = _companion(cur)
+            fork.wait_stream(cur)
+            with torch.cuda.stream(fork):
+                gw = weight_grad(x, gy, weight.shape, pad, stride)
         if ctx.needs_input_grad[0]:
             if _pair(stride) == (1, 1) and pad <= KH - 1 and pad <= KW - 1:
                 gyd, wd = gy, weight
@@ -190,7 +213,9 @@ class _Conv2dTC(torch.autograd.Function):
                     _tag = "fprop"
             else:
                 gx = input_grad_library(x, gy, weight, pad, stride)
-        if ctx.needs_input_grad[1]:
+        if fork is not None:
+            cur.wait_stream(fork)
+        elif ctx.needs_input_grad[1]:
             gw = weight_grad(x, gy, weight.shape, pad, stride)
         if want_gb:
             gb = gy.sum((0, 2, 3))
