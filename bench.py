@@ -263,6 +263,7 @@ def run_ours(args):
             graph_note = "whole step recorded once into a CUDA graph and replayed"
         except Exception as e:  # keep measuring: eager is the same arithmetic
             run = step
+            sys.stderr.write("CUDA graph capture failed: %s\n" % e)
             graph_note = "CUDA graph capture failed (%s): eager launches" % str(e).splitlines()[0][:120]
     for i in range(2):
         run(resident[i % 2])

@@ -24,8 +24,11 @@ def init_from_env(backend=None):
         backend = "nccl" if torch.cuda.is_available() else "gloo"
     if backend == "nccl":
         torch.cuda.set_device(local)
+        # NCCL writes its version / debug lines to stdout unless told otherwise; stdout is reserved for results
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if not dist.is_initialized():
-        dist.init_process_group(backend, init_method="env://")
+        kw = {"device_id": torch.device("cuda", local)} if backend == "nccl" else {}
+        dist.init_process_group(backend, init_method="env://", **kw)
     return rank, local, world
 
 
