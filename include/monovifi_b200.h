@@ -214,6 +214,10 @@ int mvf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp
 int mvf_gather_grads(float* arena, const void* const* grads, const long long* offsets, const long long* sizes, int n_tensors,
                      void* stream);
 
+/* Id of the CUDA-graph capture `stream` is part of, 0 when it is not capturing.  The host side keys its per-step caches
+ * (packed filter banks) on it so that a recorded graph never depends on buffers produced outside its own capture. */
+unsigned long long mvf_stream_capture_id(void* stream);
+
 /* device self-test: q_sequence[i] = the kernels' shared-reciprocal division of a[i] by b[i], q_ieee[i] = the
  * IEEE quotient (div.rn.f32); the two must be bit-identical for operands in the normal range. */
 int mvf_selftest_division(const float* a, const float* b, float* q_sequence, float* q_ieee, size_t n, void* stream);

@@ -351,6 +351,16 @@ int mvf_act_bwd_bias(const float* grad_y, const float* y, float* grad_pre, float
     MVF_RUN("mvf_act_bwd_bias", mvf::act_bwd_bias(grad_y, y, grad_pre, grad_bias, workspace, P, C, act, (cudaStream_t)stream));
 }
 
+unsigned long long mvf_stream_capture_id(void* stream) {
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0;
+    if (cudaStreamGetCaptureInfo((cudaStream_t)stream, &status, &id) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return status == cudaStreamCaptureStatusActive ? id : 0;
+}
+
 /* ---- fused clip_grad_norm_ + AdamW over a flat arena -------------------------------------------------------------- */
 size_t mvf_adamw_workspace_bytes(void) { return mvf::adamw_workspace_bytes(); }
 int mvf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,

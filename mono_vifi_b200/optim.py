@@ -79,6 +79,8 @@ class FlatAdamW:
             dist.all_reduce(self.G, op=dist.ReduceOp.SUM)
             self.G.mul_(1.0 / dist.get_world_size())
         st = torch.cuda.current_stream(self.P.device).cuda_stream
+        from . import conv_tc
+        conv_tc.weights_epoch += 1  # the parameters change underneath their tensors' version counters
         _lib.check(_lib.lib().mvf_adamw_step(self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(), self.V.data_ptr(), self.n,
                                              self.state.data_ptr(), self.ws.data_ptr(), self.ws.numel(), self.lr, self.betas[0],
                                              self.betas[1], self.eps, self.weight_decay, self.max_norm, st), "mvf_adamw_step")
