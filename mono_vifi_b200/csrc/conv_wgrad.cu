@@ -11,6 +11,7 @@
 // sit side by side in TMEM (taps x 32 columns <= 512).  Each CTA writes its partial sums to a workspace; a second
 // kernel adds the splits in a fixed order (deterministic) and stores dw in the [Cout,Cin,KH,KW] layout of the
 // parameter.  Replaces cuDNN's convolution_backward_weight behind nn.Conv2d of the reference's networks.
+#include <cstdlib>
 #include <mutex>
 
 #include "conv_tc.cuh"
@@ -317,7 +318,13 @@ Plan make_plan(const WgradDesc& d) {
     pl.cin_pad = (d.Cin + N_TILE - 1) / N_TILE * N_TILE;
     const int tiles = (pl.cout_pad / M_TILE) * (pl.cin_pad / N_TILE);
     // split the pixels so that about one wave of CTAs exists, but keep at least 8 patches per CTA
-    int ks = (148 + tiles - 1) / tiles;
+    static int target_ctas = 0;
+    if (target_ctas == 0) {
+        const char* e = std::getenv("MVF_WGRAD_CTAS");
+        target_ctas = e ? std::atoi(e) : 148;
+        if (target_ctas < 1) target_ctas = 148;
+    }
+    int ks = (target_ctas + tiles - 1) / tiles;
     const int max_ks = pl.n_patches / 8 > 0 ? pl.n_patches / 8 : 1;
     if (ks > max_ks) ks = max_ks;
     if (ks < 1) ks = 1;
