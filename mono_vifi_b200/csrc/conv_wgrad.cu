@@ -324,7 +324,7 @@ Plan make_plan(const WgradDesc& d) {
         target_ctas = e ? std::atoi(e) : 148;
         if (target_ctas < 1) target_ctas = 148;
     }
-    int ks = (target_ctas + tiles - 1) / tiles;
+    int ks = target_ctas / tiles;  // floor: tiles * ks <= one wave (a 150-CTA grid would cost a second wave for 2 CTAs)
     const int max_ks = pl.n_patches / 8 > 0 ? pl.n_patches / 8 : 1;
     if (ks > max_ks) ks = max_ks;
     if (ks < 1) ks = 1;
