@@ -3,6 +3,7 @@
 parameters and running statistics (state_dict unchanged) and only replaces the arithmetic; anything the kernels do not
 cover (eval mode, CPU tensors, channel counts that are not multiples of 4, cumulative-average momentum) takes the plain
 torch path `relu(bn(x) + identity)`."""
+import contextlib
 import os
 
 import torch
@@ -85,10 +86,53 @@ def usable(bn, x):
             bn.affine and bn.momentum is not None and x.dtype == torch.float32)
 
 
+# ---- deferred running statistics ------------------------------------------------------------------------------------
+# When the same BatchNorm modules are applied twice CONCURRENTLY (the two pose passes on two streams), the running
+# statistics must still see the two updates in program order.  Inside `with deferred_running_stats() as entries:` a call
+# normalises as usual but writes its batch mean / unbiased variance to a private buffer (momentum 1 into zeros) instead
+# of touching the module; apply_deferred(entries), called later on a stream that has joined both passes, replays the
+# momentum updates in order with three multi-tensor launches.
+_deferred = None
+
+
+@contextlib.contextmanager
+def deferred_running_stats():
+    global _deferred
+    prev, _deferred = _deferred, []
+    try:
+        yield _deferred
+    finally:
+        _deferred = prev
+
+
+def apply_deferred(entries):
+    if not entries:
+        return
+    with torch.no_grad():
+        groups = {}
+        for bn, tmp, m in entries:
+            g = groups.setdefault(m, ([], []))
+            C = bn.running_mean.numel()
+            g[0].extend([bn.running_mean, bn.running_var])
+            g[1].extend([tmp[:C], tmp[C:]])
+        for m, (stats, batch) in groups.items():
+            torch._foreach_mul_(stats, 1.0 - m)
+            torch._foreach_add_(stats, batch, alpha=m)
+        counters = [bn.num_batches_tracked for bn, _, _ in entries if bn.num_batches_tracked is not None]
+        if counters:
+            torch._foreach_add_(counters, 1)
+    entries.clear()
+
+
 def bn_act(bn, x, identity=None, relu=True):
     """relu(bn(x) + identity) with nn.BatchNorm2d `bn` (its parameters / buffers are used and updated in place)."""
     if usable(bn, x):
         rm, rv, nbt = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if bn.track_running_stats else (None, None, None)
+        if rm is not None and _deferred is not None:
+            C = rm.numel()
+            tmp = torch.zeros(2 * C, device=x.device, dtype=torch.float32)
+            _deferred.append((bn, tmp, float(bn.momentum)))
+            return _BNAct.apply(x, identity, bn.weight, bn.bias, tmp[:C], tmp[C:], None, float(bn.eps), 1.0, bool(relu))
         if nbt is not None and nbt.dtype != torch.int64:
             nbt.add_(1)
             nbt = None

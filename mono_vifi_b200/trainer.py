@@ -12,6 +12,7 @@ import torch
 
 from . import layers as L
 from . import networks as N
+from . import bn_act
 from .ddp import FlatGradAllReduce
 from .fused import fused_photometric_loss
 
@@ -123,7 +124,7 @@ class _Fork:
                 t.record_stream(self.cur)
 
 
-def single_frame_losses(models, inputs, opt, side=None):
+def single_frame_losses(models, inputs, opt, side=None, side2=None):
     """The single-frame slice of process_batch: train.py:728-729 (poses), 736 + 739 (depth), 747-750 (loss).
     The pose branch and the depth branch are independent until the loss: with `side` (a CUDA stream) the two pose
     passes run there while the depth network runs on the current stream, so their short kernels (1-3 tiles per SM, many
@@ -132,9 +133,19 @@ def single_frame_losses(models, inputs, opt, side=None):
     K, inv_K = inputs[("K", 0)], inputs[("inv_K", 0)]
     with _Fork(side) as fork:
         pose_n1_0, pose_0_n1 = predict_poses(models, inputs[("color_aug", -1, 0)], inputs[("color_aug", 0, 0)])
-        pose_0_p1, pose_p1_0 = predict_poses(models, inputs[("color_aug", 0, 0)], inputs[("color_aug", 1, 0)])
+    # the second pose pass shares its weights with the first; on its own stream (side2) it defers its BatchNorm
+    # running-statistics updates, which are replayed in program order once both passes have been joined
+    with _Fork(side2 if side2 is not None else side) as fork2:
+        if side2 is not None:
+            with bn_act.deferred_running_stats() as deferred:
+                pose_0_p1, pose_p1_0 = predict_poses(models, inputs[("color_aug", 0, 0)], inputs[("color_aug", 1, 0)])
+        else:
+            deferred = None
+            pose_0_p1, pose_p1_0 = predict_poses(models, inputs[("color_aug", 0, 0)], inputs[("color_aug", 1, 0)])
     disp_0 = models["depth"](models["encoder"](inputs[("color_aug", 0, 0)]))[("disp", 0)]
-    fork.join(pose_0_n1, pose_0_p1)
+    fork.join(pose_0_n1)
+    fork2.join(pose_0_p1)
+    bn_act.apply_deferred(deferred)
     loss, auto_mask = loss_group(opt, disp_0, img_0, pose_0_n1, pose_0_p1, img_n1, img_p1, K, inv_K)
     return {"loss": loss, "loss_base": loss, "disp": disp_0, "auto_mask": auto_mask}
 
@@ -218,9 +229,14 @@ class TrainStep:
         # accumulator to the stream of its first use; binding them to the legacy default stream would make the step
         # impossible to record into a CUDA graph later (GraphedTrainStep).
         self.stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
-        # second stream for the pose branch of the single-frame step (MVF_SIDE_STREAM=0 serialises everything)
+        # streams for the two pose passes of the single-frame step (MVF_SIDE_STREAM=1: both on one, 0: everything serial)
         self.side = (torch.cuda.Stream(device=device)
-                     if device.type == "cuda" and os.environ.get("MVF_SIDE_STREAM", "1") != "0" else None)
+                     if device.type == "cuda" and os.environ.get("MVF_SIDE_STREAM", "2") != "0" else None)
+        self.side2 = (torch.cuda.Stream(device=device)
+                      if self.side is not None and os.environ.get("MVF_SIDE_STREAM", "2") == "2" else None)
+        if self.side2 is not None and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            # the shared pose weights receive gradients from two streams on purpose
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
 
     def train(self):
         for m in self.models.values():
@@ -236,10 +252,11 @@ class TrainStep:
         if self.opt.multi_frame:
             out = multi_frame_losses(self.models, self.vfi, inputs, self.opt)
         else:
-            out = single_frame_losses(self.models, inputs, self.opt, side=self.side)
+            out = single_frame_losses(self.models, inputs, self.opt, side=self.side, side2=self.side2)
         out["loss"].backward()
-        if self.side is not None:  # parameter gradients of the pose branch were produced on the side stream
-            torch.cuda.current_stream(self.device).wait_stream(self.side)
+        for st in (self.side, self.side2):  # parameter gradients of the pose branch were produced on the side streams
+            if st is not None:
+                torch.cuda.current_stream(self.device).wait_stream(st)
         if self.reducer is not None:
             self.reducer.allreduce_mean()
         return out
