@@ -55,6 +55,42 @@ struct ConvArgs {
     float* dbg;                  // debug: raw copy of pipeline stage 0 (A then B) of CTA (0,0); null in production
 };
 
+// ---- epilogue arithmetic: v[0..CH) += bias[n_first ..], then the activation ---------------------------------------
+// ELU's exp(t) - 1 for t <= 0: ex2.approx based, with the cubic Taylor polynomial where cancellation would cost accuracy
+// (|t| < 1/16: polynomial error < 7e-7 relative; elsewhere the subtraction loses at most ~4 bits of a 2-ulp exp) --
+// far inside the TF32 product error of the convolution it follows, and 5 instructions instead of expm1f's ~35.
+__device__ __forceinline__ float elu_neg(float t) {
+    const float e = __expf(t) - 1.0f;
+    const float q = t * fmaf(t, fmaf(t, 0.16666667f, 0.5f), 1.0f) + t * t * t * t * 0.041666668f;
+    return t > -0.0625f ? q : e;
+}
+
+// Branches are on kernel-uniform values only and sit OUTSIDE the element loops (the per-element form cost ~30
+// instructions per value: it was 40 % of the stall samples of the 16-channel decoder layers).
+template <int CH>
+__device__ __forceinline__ void bias_act(float (&v)[CH], const float* __restrict__ bias, int n_first, int Cout, int act) {
+    if (bias) {
+        if (n_first + CH <= Cout && ((reinterpret_cast<uintptr_t>(bias + n_first) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n_first + j));
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+                if (n_first + j < Cout) v[j] += __ldg(bias + n_first + j);
+        }
+    }
+    if (act == 1) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == 2) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = v[j] > 0.f ? v[j] : elu_neg(v[j]);
+    }
+}
+
 template <int N_TILE>
 __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA,
                                                               const __grid_constant__ CUtensorMap mapB, const ConvArgs p) {
@@ -155,14 +191,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
             if (!pix_ok) continue;
             float v[CH];
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                const int n = n0 + c0 + j;
-                float t = __uint_as_float(r[j]);
-                if (p.bias && n < p.Cout) t += __ldg(p.bias + n);
-                if (p.act == 1) t = fmaxf(t, 0.f);
-                else if (p.act == 2) t = t > 0.f ? t : expm1f(t);
-                v[j] = t;
-            }
+            for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+            bias_act<CH>(v, p.bias, n0 + c0, p.Cout, p.act);
             if (vec_ok) {
 #pragma unroll
                 for (int j = 0; j < CH; j += 4)
@@ -210,6 +240,7 @@ struct PatchArgs {
     int P, PWo, TR, R;           // patch pitch, valid output columns per row, output rows per 128-position tile, patch rows
     int nseg, tiles_y;           // column segments per image row, CTA rows per image
     int n_cblk, act;
+    int kg_last;                 // 8-channel MMA groups that hold real channels in the LAST 32-channel block (1..4)
     int patch_bytes, patch_stride;  // bytes landed per patch, distance between the two patch buffers (1024-aligned)
     int n_mtiles, n_tiles;       // M tiles (B * nseg * tiles_y), all tiles (M tiles x N tiles)
     int b_resident;              // 1: the whole filter bank of the CTA's couts fits in the ring and is loaded ONCE per CTA
@@ -325,6 +356,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
                 mbar_wait(&a_full[ab], aph);
                 const uint32_t a_base = smA_u + (uint32_t)(ab * p.patch_stride);
                 int kh = 0, kw = 0;
+                const int ng = (cb == p.n_cblk - 1) ? p.kg_last : KGROUPS;  // all-zero channel groups are not multiplied
                 for (int tp = 0; tp < taps; ++tp) {
                     if (!p.b_resident) mbar_wait(&b_full[bs], bph);
                     tc_fence_after();
@@ -338,8 +370,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
                             const uint32_t a_lo = ((a_base + (uint32_t)((mt * p.TR + kh) * p.P + kw) * 128u) >> 4) | (uint32_t)desc_hi;
 #pragma unroll
                             for (int kg = 0; kg < KGROUPS; ++kg)
-                                umma_tf32(d_base + (uint32_t)(mt * N_TILE), d_up | (uint64_t)(a_lo + 2 * kg),
-                                          d_up | (uint64_t)(b_lo + 2 * kg), idesc, (cb > 0 || tp > 0 || kg > 0) ? 1u : 0u);
+                                if (kg < ng)
+                                    umma_tf32(d_base + (uint32_t)(mt * N_TILE), d_up | (uint64_t)(a_lo + 2 * kg),
+                                              d_up | (uint64_t)(b_lo + 2 * kg), idesc, (cb > 0 || tp > 0 || kg > 0) ? 1u : 0u);
                         }
                         if (!p.b_resident) umma_commit(&b_empty[bs]);
                     }
@@ -387,14 +420,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
                     if (n0 + c0 >= p.Cout) continue;  // (uniform) slab entirely past Cout
                     float v[SLAB];
 #pragma unroll
-                    for (int jj = 0; jj < SLAB; ++jj) {
-                        const int n = n0 + c0 + jj;
-                        float tval = __uint_as_float(rr[jj]);
-                        if (p.bias && n < p.Cout) tval += __ldg(p.bias + n);
-                        if (p.act == 1) tval = fmaxf(tval, 0.f);
-                        else if (p.act == 2) tval = tval > 0.f ? tval : expm1f(tval);
-                        v[jj] = tval;
-                    }
+                    for (int jj = 0; jj < SLAB; ++jj) v[jj] = __uint_as_float(rr[jj]);
+                    bias_act<SLAB>(v, p.bias, n0 + c0, p.Cout, p.act);
                     if (use_tma) {
                         // the staging buffer must have been read by the TMA store issued two slabs ago
                         if (et == 0) tma_store_wait_read<1>();
@@ -606,6 +633,7 @@ static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const f
     a.n_tiles = a.n_mtiles * n_ntiles;
     const int slab = n_tile < 32 ? n_tile : 32;
     const int nb_ring = n_tile >= 128 ? 4 : (n_tile >= 64 ? 8 : 16);
+    a.kg_last = ((d.Cin - (a.n_cblk - 1) * BLOCK_K) + 7) / 8;
     a.b_resident = (n_ntiles == 1 && d.KH * d.KW * a.n_cblk <= nb_ring && !getenv("MVF_CONV_NO_RESIDENT")) ? 1 : 0;
     if (nb_ring * n_tile * BLOCK_K * 4 + 2 * TILE_M * slab * 4 + 2 * a.patch_stride + 1280 > 227 * 1024) {
         *why = "patch does not fit in shared memory";
