@@ -240,6 +240,7 @@ struct PatchArgs {
     int P, PWo, TR, R;           // patch pitch, valid output columns per row, output rows per 128-position tile, patch rows
     int nseg, tiles_y;           // column segments per image row, CTA rows per image
     int n_cblk, act;
+    int nb;                      // filter-ring slots in use (<= NB): as many as shared memory allows, TMA latency is what they hide
     int kg_last;                 // 8-channel MMA groups that hold real channels in the LAST 32-channel block (1..4)
     int patch_bytes, patch_stride;  // bytes landed per patch, distance between the two patch buffers (1024-aligned)
     int n_mtiles, n_tiles;       // M tiles (B * nseg * tiles_y), all tiles (M tiles x N tiles)
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
     constexpr int SLAB = N_TILE < 32 ? N_TILE : 32;      // output channels per staged slab (one TMA-store box row = SLAB floats)
     constexpr int STAGE_OUT_BYTES = TILE_M * SLAB * 4;   // 16 KB (8 KB for 16-channel tiles)
     unsigned char* smB = smem;
-    unsigned char* smO = smem + NB * B_STAGE_BYTES;      // two output staging buffers
+    unsigned char* smO = smem + p.nb * B_STAGE_BYTES;    // two output staging buffers (p.nb <= NB ring slots in use)
     unsigned char* smA = smO + 2 * STAGE_OUT_BYTES;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smA + 2 * p.patch_stride);
     uint64_t* a_empty = a_full + 2;
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
                             mbar_arrive_expect_tx(&b_full[bs], B_STAGE_BYTES);
                             tma_load_3d(smB + bs * B_STAGE_BYTES, &mapB, &b_full[bs], 0, n0, kb);
                         }
-                        if (++bs == NB) { bs = 0; bph ^= 1; }
+                        if (++bs == p.nb) { bs = 0; bph ^= 1; }
                     }
                 }
             }
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
                         if (!p.b_resident) umma_commit(&b_empty[bs]);
                     }
                     __syncwarp();
-                    if (++bs == NB) { bs = 0; bph ^= 1; }
+                    if (++bs == p.nb) { bs = 0; bph ^= 1; }
                     if (++kw == p.KW) { kw = 0; ++kh; }
                 }
                 if (elect_one()) umma_commit(&a_empty[ab]);
@@ -537,8 +538,8 @@ cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const ConvA
 template <int N_TILE, int MT>
 cudaError_t launch_patch(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapY, const PatchArgs& a,
                          cudaStream_t st) {
-    constexpr int NB = (N_TILE >= 128) ? 4 : (N_TILE >= 64 ? 8 : 16);  // 64 / 64 / 64 / 32 KB of filter tiles
-    const int smem = NB * N_TILE * BLOCK_K * 4 + 2 * TILE_M * (N_TILE < 32 ? N_TILE : 32) * 4 + 2 * a.patch_stride + 1024 + 256;
+    constexpr int NB = (N_TILE >= 128) ? 8 : 16;  // ring slots (barriers); a.nb of them are backed by shared memory
+    const int smem = a.nb * N_TILE * BLOCK_K * 4 + 2 * TILE_M * (N_TILE < 32 ? N_TILE : 32) * 4 + 2 * a.patch_stride + 1024 + 256;
     static int attr_max = 0;
     if (smem > attr_max) {
         cudaError_t e = cudaFuncSetAttribute(conv_patch_kernel<N_TILE, MT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -632,10 +633,15 @@ static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const f
     a.n_mtiles = d.B * a.nseg * a.tiles_y;
     a.n_tiles = a.n_mtiles * n_ntiles;
     const int slab = n_tile < 32 ? n_tile : 32;
-    const int nb_ring = n_tile >= 128 ? 4 : (n_tile >= 64 ? 8 : 16);
+    // filter ring: up to 8 x 16 KB (N = 128) / 16 slots (narrower tiles), limited by what the patches leave free
+    const int nb_max = n_tile >= 128 ? 8 : 16;
+    int nb_ring = (227 * 1024 - 1280 - 2 * TILE_M * slab * 4 - 2 * a.patch_stride) / (n_tile * BLOCK_K * 4);
+    if (nb_ring > nb_max) nb_ring = nb_max;
+    if (const char* e = getenv("MVF_CONV_NB")) nb_ring = atoi(e) < nb_ring ? atoi(e) : nb_ring;
+    a.nb = nb_ring;
     a.kg_last = ((d.Cin - (a.n_cblk - 1) * BLOCK_K) + 7) / 8;
     a.b_resident = (n_ntiles == 1 && d.KH * d.KW * a.n_cblk <= nb_ring && !getenv("MVF_CONV_NO_RESIDENT")) ? 1 : 0;
-    if (nb_ring * n_tile * BLOCK_K * 4 + 2 * TILE_M * slab * 4 + 2 * a.patch_stride + 1280 > 227 * 1024) {
+    if (nb_ring < 2) {
         *why = "patch does not fit in shared memory";
         return cudaErrorInvalidValue;
     }

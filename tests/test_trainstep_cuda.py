@@ -204,8 +204,11 @@ def test_flat_adamw_matches_torch():
 
 def test_concurrent_streams_match_the_serial_step():
     """The step with the pose passes on two side streams (deferred BatchNorm running statistics) and weight gradients on
-    companion streams must produce what the one-stream step produces: same losses, same parameters, same BatchNorm
-    buffers (the two momentum updates of the shared pose encoder in program order), eagerly and as a CUDA graph."""
+    companion streams must produce what the one-stream step produces: same loss, same parameter gradients, same
+    BatchNorm buffers (the two momentum updates of the shared pose encoder in program order) -- eagerly and as a CUDA
+    graph.  Gradients are compared BEFORE the optimiser (Adam turns rounding noise on near-zero gradients into
+    step-sized parameter differences); the cuDNN strided data-gradient kernels still used for the stride-2 layers are
+    not bitwise reproducible, so the serial step is also run twice to measure that noise floor."""
     import copy
     import torch
     from mono_vifi_b200 import conv_tc, trainer as TR
@@ -214,7 +217,8 @@ def test_concurrent_streams_match_the_serial_step():
     torch.manual_seed(5)
     base = TR.build_models(opt, dev)
     inputs = TR.synthetic_inputs(opt, dev, seed=4)
-    def run(serial, graphed):
+
+    def run(serial, graphed=False):
         models = copy.deepcopy(base)
         step = TR.TrainStep(opt, dev, models=models)
         step.train()
@@ -224,27 +228,44 @@ def test_concurrent_streams_match_the_serial_step():
         conv_tc.wgrad_stream_enabled = not serial
         try:
             torch.manual_seed(77)  # the tie-break noise is drawn inside the step
-            runner = TR.GraphedTrainStep(step, inputs, warmup=2) if graphed else step
-            losses = [float(runner(inputs)) for _ in range(2)]
+            if graphed:
+                runner = TR.GraphedTrainStep(step, inputs, warmup=2)
+                losses = [float(runner(inputs)) for _ in range(2)]
+                torch.cuda.synchronize()
+                return losses, None, models
+            cur = torch.cuda.current_stream(dev)
+            step.stream.wait_stream(cur)
+            with torch.cuda.stream(step.stream):
+                out = step.forward_backward(inputs)
+            cur.wait_stream(step.stream)
             torch.cuda.synchronize()
+            grads = {id_: (None if p.grad is None else p.grad.detach().clone()) for id_, p in enumerate(step.params)}
+            return float(out["loss"]), grads, models
         finally:
             conv_tc.wgrad_stream_enabled = saved
-        return losses, models
 
-    ref_losses, ref_models = run(serial=True, graphed=False)
-    for graphed in (False, True):
-        losses, models = run(serial=False, graphed=graphed)
-        if not graphed:
-            assert losses == pytest.approx(ref_losses, rel=1e-5)
-        for name in ref_models:
-            for (k, a), (_, b) in zip(ref_models[name].state_dict().items(), models[name].state_dict().items()):
-                if graphed and not a.dtype.is_floating_point:
-                    continue  # the graphed runner takes extra warm-up steps: counters differ by construction
-                if not graphed:
-                    assert torch.allclose(a.float(), b.float(), rtol=1e-4, atol=1e-5), (name, k)
-        if graphed:
-            # 2 eager + 1 capture + 2 replays on one side, so only check sanity of the graphed run here
-            assert all(np.isfinite(l) for l in losses)
-            for m in models.values():
-                for k, v in m.state_dict().items():
-                    assert torch.isfinite(v.float()).all(), k
+    def worst(ga, gb):
+        w = 0.0
+        for k in ga:
+            assert (ga[k] is None) == (gb[k] is None)
+            if ga[k] is not None:
+                scale = float(ga[k].abs().max())
+                if scale > 0:
+                    w = max(w, float((ga[k] - gb[k]).abs().max()) / scale)
+        return w
+
+    loss_a, g_a, m_a = run(serial=True)
+    loss_b, g_b, _ = run(serial=True)
+    loss_c, g_c, m_c = run(serial=False)
+    floor = worst(g_a, g_b)
+    assert loss_c == pytest.approx(loss_a, rel=1e-6)
+    assert worst(g_a, g_c) <= max(1e-5, 20 * floor), (worst(g_a, g_c), floor)
+    for name in m_a:  # BatchNorm buffers after one forward: deferred in-order updates == in-place updates
+        for (k, a), (_, b) in zip(m_a[name].state_dict().items(), m_c[name].state_dict().items()):
+            if "running_" in k or "num_batches" in k:
+                assert torch.allclose(a.float(), b.float(), rtol=1e-5, atol=1e-6), (name, k)
+    losses, _, models = run(serial=False, graphed=True)
+    assert all(np.isfinite(l) for l in losses)
+    for m in models.values():
+        for k, v in m.state_dict().items():
+            assert torch.isfinite(v.float()).all(), k
