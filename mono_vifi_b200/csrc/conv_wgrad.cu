@@ -38,6 +38,7 @@ struct WgradArgs {
     int n_patches;   // B * patches_y * patches_x
     int ksplit;
     int cout_pad, cin_pad;
+    int fuse_row;      // 1: one MMA of N = KW * 32 per filter row (needs shared_patch)
     int shared_patch;  // 1 (stride 1, ph == 1): ONE haloed x patch per stage serves all taps; 0: one x box per tap
     int pwx;           // shared patch: its pitch in pixels (pw + KW - 1)
     int stage_bytes, a_bytes, b_bytes;  // stage stride (1024-aligned), bytes landed for A and for B (all taps)
@@ -130,7 +131,27 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
             const uint32_t a_lo = ((smem_u + (uint32_t)(s * p.stage_bytes)) >> 4) | (uint32_t)a_hi;
             const uint32_t b_lo = (((smem_u + (uint32_t)(s * p.stage_bytes)) >> 4) + ((uint32_t)p.a_bytes >> 4)) | (uint32_t)b_hi;
             const uint64_t a_up = a_hi & 0xFFFFFFFF00000000ull, b_up = b_hi & 0xFFFFFFFF00000000ull;
-            if (elect_one()) {
+            if (p.fuse_row) {
+                // One MMA per filter ROW: the KW taps of a row read the x patch shifted by one pixel (128 bytes) each, so
+                // they are KW consecutive 32-channel atoms of ONE MN-major B operand whose atom stride (LBO) is 128 B --
+                // N = KW * 32.  The tensor core accepts one tcgen05.mma per ~70 cycles however small it is; an N = 32
+                // MMA is 16 cycles of work (ncu: tensor pipe 21 % active), an N = 96 one 48.  Accumulator columns come
+                // out in the same order ((kh * KW + kw) * 32 + ci) as with one MMA per tap.
+                if (elect_one()) {
+                    const uint32_t idesc_row = make_idesc_tf32(M_TILE, p.KW * N_TILE, 1, 1);
+                    const uint64_t brow_up = make_smem_desc(0, 128, 512, SWZ_128B_BASE32B) & 0xFFFFFFFF00000000ull;
+                    const uint32_t brow_lo = (b_lo & 0x3FFFu) | (uint32_t)(make_smem_desc(0, 128, 512, SWZ_128B_BASE32B) & 0xFFFFC000ull);
+                    for (int kh = 0; kh < p.KH; ++kh) {
+                        const uint32_t bt = brow_lo + (uint32_t)(kh * p.pwx * 8);
+                        const uint32_t dcol = tmem_d + (uint32_t)(kh * p.KW * N_TILE);
+#pragma unroll 4
+                        for (int kk = 0; kk < kmma; ++kk)
+                            umma_tf32(dcol, a_up | (uint64_t)(a_lo + kk * 64), brow_up | (uint64_t)(bt + kk * 64), idesc_row,
+                                      (it > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+            } else if (elect_one()) {
                 int kh = 0, kw = 0;
                 for (int t = 0; t < taps; ++t) {
                     // tap t: its own box, or the shared patch shifted by kh rows and kw pixels (whole 128-byte rows)
@@ -374,6 +395,7 @@ cudaError_t conv_wgrad(const WgradDesc& d, const float* x, const float* gy, floa
     a.Ho = pl.Ho; a.Wo = pl.Wo; a.B = d.B;
     a.pw = pl.pw; a.ph = pl.ph; a.patches_x = pl.patches_x; a.patches_y = pl.patches_y; a.n_patches = pl.n_patches;
     a.stages = pl.stages;
+    a.fuse_row = (pl.shared_patch && d.KW > 1 && d.KW * N_TILE <= 256 && (d.KW * N_TILE) % 16 == 0 && !getenv("MVF_WGRAD_NO_FUSE")) ? 1 : 0;
     a.shared_patch = pl.shared_patch; a.pwx = pl.pwx; a.stage_bytes = pl.stage_bytes; a.a_bytes = pl.a_bytes; a.b_bytes = pl.b_bytes;
     a.ksplit = pl.ksplit; a.cout_pad = pl.cout_pad; a.cin_pad = pl.cin_pad;
 
