@@ -10,6 +10,8 @@
 // (grad_y, y, x) twice and writes grad_x [+ grad_identity].  Per-channel sums are accumulated per CTA, written to a
 // workspace and added in a fixed order by a small finalize kernel (double precision): bitwise deterministic.
 #include "bn_cl.cuh"
+
+#include <cstdlib>
 #include "pdl.cuh"
 
 namespace mvf {
@@ -243,8 +245,15 @@ __global__ void bias_finalize_kernel(const float* __restrict__ partial, int nblo
 
 int partial_blocks(long long P, int C4) {
     const int rows = NT / C4 > 0 ? NT / C4 : 1;
-    long long nb = (P + (long long)rows * 16 - 1) / ((long long)rows * 16);  // at least ~16 pixels per thread
-    if (nb > 148 * 2) nb = 148 * 2;
+    static int per_sm = 0, min_px = 0;
+    if (per_sm == 0) {
+        const char* e = std::getenv("MVF_BN_BLOCKS_PER_SM");
+        per_sm = e ? std::atoi(e) : 4;
+        const char* m = std::getenv("MVF_BN_MIN_PX");
+        min_px = m ? std::atoi(m) : 16;
+    }
+    long long nb = (P + (long long)rows * min_px - 1) / ((long long)rows * min_px);  // at least ~min_px pixels per thread
+    if (nb > 148 * per_sm) nb = 148 * per_sm;
     if (nb < 1) nb = 1;
     return (int)nb;
 }

@@ -38,7 +38,7 @@ struct WgradArgs {
     int n_patches;   // B * patches_y * patches_x
     int ksplit;
     int cout_pad, cin_pad;
-    int fuse_row;      // 1: one MMA of N = KW * 32 per filter row (needs shared_patch)
+    int fuse_row;      // > 0: taps per MMA (N = fuse_row * 32): KW with a shared patch, a divisor of taps <= 8 otherwise
     int shared_patch;  // 1 (stride 1, ph == 1): ONE haloed x patch per stage serves all taps; 0: one x box per tap
     int pwx;           // shared patch: its pitch in pixels (pw + KW - 1)
     int stage_bytes, a_bytes, b_bytes;  // stage stride (1024-aligned), bytes landed for A and for B (all taps)
@@ -132,18 +132,22 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
             const uint32_t b_lo = (((smem_u + (uint32_t)(s * p.stage_bytes)) >> 4) + ((uint32_t)p.a_bytes >> 4)) | (uint32_t)b_hi;
             const uint64_t a_up = a_hi & 0xFFFFFFFF00000000ull, b_up = b_hi & 0xFFFFFFFF00000000ull;
             if (p.fuse_row) {
-                // One MMA per filter ROW: the KW taps of a row read the x patch shifted by one pixel (128 bytes) each, so
-                // they are KW consecutive 32-channel atoms of ONE MN-major B operand whose atom stride (LBO) is 128 B --
-                // N = KW * 32.  The tensor core accepts one tcgen05.mma per ~70 cycles however small it is; an N = 32
-                // MMA is 16 cycles of work (ncu: tensor pipe 21 % active), an N = 96 one 48.  Accumulator columns come
-                // out in the same order ((kh * KW + kw) * 32 + ci) as with one MMA per tap.
+                // One MMA per GROUP of `fuse_row` taps.  Shared patch: the KW taps of a filter row read the x patch
+                // shifted by one pixel (128 bytes) each; per-tap boxes: consecutive taps are kp * 128 bytes apart.  Either
+                // way the group is `fuse_row` 32-channel atoms of ONE MN-major B operand with a constant atom stride
+                // (LBO), N = fuse_row * 32.  The tensor core accepts one tcgen05.mma per ~70 cycles however small it is:
+                // an N = 32 MMA is 16 cycles of work (ncu: tensor pipe 21 % active), an N = 96 one 48.  Accumulator
+                // columns come out in the same order (tap * 32 + ci) as with one MMA per tap.
                 if (elect_one()) {
-                    const uint32_t idesc_row = make_idesc_tf32(M_TILE, p.KW * N_TILE, 1, 1);
-                    const uint64_t brow_up = make_smem_desc(0, 128, 512, SWZ_128B_BASE32B) & 0xFFFFFFFF00000000ull;
-                    const uint32_t brow_lo = (b_lo & 0x3FFFu) | (uint32_t)(make_smem_desc(0, 128, 512, SWZ_128B_BASE32B) & 0xFFFFC000ull);
-                    for (int kh = 0; kh < p.KH; ++kh) {
-                        const uint32_t bt = brow_lo + (uint32_t)(kh * p.pwx * 8);
-                        const uint32_t dcol = tmem_d + (uint32_t)(kh * p.KW * N_TILE);
+                    const uint32_t idesc_row = make_idesc_tf32(M_TILE, p.fuse_row * N_TILE, 1, 1);
+                    const uint32_t lbo = p.shared_patch ? 128u : (uint32_t)kp * 128u;
+                    const uint64_t brow = make_smem_desc(0, lbo, 512, SWZ_128B_BASE32B);
+                    const uint64_t brow_up = brow & 0xFFFFFFFF00000000ull;
+                    const uint32_t brow_lo = (b_lo & 0x3FFFu) | (uint32_t)(brow & 0xFFFFC000ull);
+                    const int groups = taps / p.fuse_row;
+                    for (int kh = 0; kh < groups; ++kh) {
+                        const uint32_t bt = brow_lo + (uint32_t)(p.shared_patch ? kh * p.pwx * 8 : kh * p.fuse_row * kp * 8);
+                        const uint32_t dcol = tmem_d + (uint32_t)(kh * p.fuse_row * N_TILE);
 #pragma unroll 4
                         for (int kk = 0; kk < kmma; ++kk)
                             umma_tf32(dcol, a_up | (uint64_t)(a_lo + kk * 64), brow_up | (uint64_t)(bt + kk * 64), idesc_row,
@@ -395,7 +399,15 @@ cudaError_t conv_wgrad(const WgradDesc& d, const float* x, const float* gy, floa
     a.Ho = pl.Ho; a.Wo = pl.Wo; a.B = d.B;
     a.pw = pl.pw; a.ph = pl.ph; a.patches_x = pl.patches_x; a.patches_y = pl.patches_y; a.n_patches = pl.n_patches;
     a.stages = pl.stages;
-    a.fuse_row = (pl.shared_patch && d.KW > 1 && d.KW * N_TILE <= 256 && (d.KW * N_TILE) % 16 == 0 && !getenv("MVF_WGRAD_NO_FUSE")) ? 1 : 0;
+    a.fuse_row = 0;
+    if (!getenv("MVF_WGRAD_NO_FUSE")) {
+        if (pl.shared_patch) {
+            if (d.KW > 1 && d.KW * N_TILE <= 256) a.fuse_row = d.KW;
+        } else if (pl.pw * pl.ph * 128 <= (0x3FFF << 4)) {  // the atom stride must fit the 14-bit LBO field
+            for (int g = 8; g > 1; --g)
+                if ((d.KH * d.KW) % g == 0) { a.fuse_row = g; break; }
+        }
+    }
     a.shared_patch = pl.shared_patch; a.pwx = pl.pwx; a.stage_bytes = pl.stage_bytes; a.a_bytes = pl.a_bytes; a.b_bytes = pl.b_bytes;
     a.ksplit = pl.ksplit; a.cout_pad = pl.cout_pad; a.cin_pad = pl.cin_pad;
 
