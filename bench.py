@@ -144,7 +144,7 @@ def run_reference(args):
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -363,12 +363,36 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         r = time_cpu(args.cpu_batch, args.height, args.width, 3, 1, budget_s=25.0)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
+
+
+_RESULT_FD = None
+
+
+def _reserve_stdout():
+    """stdout carries exactly one JSON line.  Native libraries (NCCL's version banner, cuDNN warnings) printf to fd 1,
+    so fd 1 is pointed at stderr for the whole run and the result line is written to a private duplicate of the
+    original stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
     args = parse()
+    _reserve_stdout()
     if args.impl == "reference":
         return run_reference(args)
     rc = run_ours(args)
