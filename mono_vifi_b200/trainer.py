@@ -228,7 +228,10 @@ class TrainStep:
         # All training work runs on one dedicated (non-default) stream.  autograd binds each parameter's gradient
         # accumulator to the stream of its first use; binding them to the legacy default stream would make the step
         # impossible to record into a CUDA graph later (GraphedTrainStep).
-        self.stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+        # The depth branch + loss + optimiser (main stream) is the longest chain of the step; with MVF_STREAM_PRIORITY=1 it
+        # gets a higher scheduling priority than the pose streams and the weight-gradient companions that share the SMs.
+        prio = -1 if os.environ.get("MVF_STREAM_PRIORITY", "0") == "1" else 0
+        self.stream = torch.cuda.Stream(device=device, priority=prio) if device.type == "cuda" else None
         # streams for the two pose passes of the single-frame step (MVF_SIDE_STREAM=1: both on one, 0: everything serial)
         self.side = (torch.cuda.Stream(device=device)
                      if device.type == "cuda" and os.environ.get("MVF_SIDE_STREAM", "2") != "0" else None)
