@@ -12,6 +12,7 @@ import torch
 
 from . import layers as L
 from . import networks as N
+from . import affine as A
 from . import bn_act
 from .ddp import FlatGradAllReduce
 from .fused import fused_photometric_loss
@@ -34,6 +35,7 @@ class Options:
         self.lamda = 0.2                        # weight of the depth-consistency loss (options.py:92-95)
         self.multi_frame = False                # False: the single-frame slice (BASELINE configs[1]); True: full process_batch
         self.tie_break_noise = True  # train.py:1023: torch.randn * 1e-5 on the identity terms
+        self.use_affine = False      # the affine-augmentation branch of process_batch (train.py:815-883, options.py:96-99)
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError("unknown option %r" % k)
@@ -151,7 +153,7 @@ def single_frame_losses(models, inputs, opt, side=None, side2=None):
 
 
 def multi_frame_losses(models, vfi, inputs, opt):
-    """The full process_batch of the reference without the affine branch (train.py:698-814, 885): three VFI passes
+    """The full process_batch of the reference (train.py:698-885; the affine branch with opt.use_affine): three VFI passes
     (frozen IFRNet), six pose passes, single-frame depth of the target and of the two synthesized frames, fused
     multi-frame depth of the same three, six photometric loss groups (each ONE fused kernel launch) and three
     scale-invariant log depth-consistency terms.  loss = loss_base + lamda * loss_dc."""
@@ -191,6 +193,28 @@ def multi_frame_losses(models, vfi, inputs, opt):
     depth = lambda d: L.disp_to_depth(d, opt.min_depth, opt.max_depth)[1]
     loss_dc = L.si_log_depth_loss(depth(disp_0), depth(disp_0_f)) + L.si_log_depth_loss(depth(disp_nt), depth(disp_nt_f)) + \
         L.si_log_depth_loss(depth(disp_pt), depth(disp_pt_f))
+    if opt.use_affine:
+        # train.py:815-883: the single-frame network on the rotated / cropped / rescaled view of each of the three frames;
+        # poses conjugated by Rc, photometric loss masked by valid_mask_rec, and two scale-aware depth-consistency terms
+        # against the un-augmented single-frame and fused depths.  Batched transforms: affine.py (no .item() syncs).
+        Rc, angle, box, ratio = inputs["Rc"], inputs["angle"], inputs["box"], inputs["ratio_local"]
+        mask_rec, mask_cons = inputs["valid_mask_rec"], inputs["valid_mask_cons"]
+        aff_n1, aff_0, aff_p1 = inputs[("color_affine", -1, 0)], inputs[("color_affine", 0, 0)], inputs[("color_affine", 1, 0)]
+        conj = lambda T: A.conjugate_pose(T, Rc)
+
+        def affine_terms(net_in, tgt, T_n1, T_p1, disp_single, disp_fused):
+            disp_a = dec(keep(enc(net_in)))[("disp", 0)]
+            lb = loss_group(opt, disp_a, tgt, conj(T_n1), conj(T_p1), aff_n1, aff_p1, K, inv_K, mask_rec=mask_rec)[0]
+            restore = A.depth_restore(depth(disp_a), angle, box, ratio)
+            return lb, (L.si_log_depth_loss(restore, depth(disp_fused), mask_cons) +
+                        L.si_log_depth_loss(restore, depth(disp_single), mask_cons))
+
+        img_nt_a, img_pt_a = A.affine_transform(img_nt, angle, box), A.affine_transform(img_pt, angle, box)
+        for net_in, tgt, T_n1, T_p1, d_s, d_f in ((inputs[("color_affine_aug", 0, 0)], aff_0, pose_0_n1, pose_0_p1, disp_0, disp_0_f),
+                                                  (img_nt_a, img_nt_a, pose_nt_n1, pose_nt_p1, disp_nt, disp_nt_f),
+                                                  (img_pt_a, img_pt_a, pose_pt_n1, pose_pt_p1, disp_pt, disp_pt_f)):
+            lb, ldc = affine_terms(net_in, tgt, T_n1, T_p1, d_s, d_f)
+            loss_base, loss_dc = loss_base + lb, loss_dc + ldc
     return {"loss": loss_base + opt.lamda * loss_dc, "loss_base": loss_base, "loss_dc": loss_dc, "disp": disp_0,
             "disp_fuse": disp_0_f}
 
@@ -378,6 +402,35 @@ def synthetic_inputs(opt, device=None, seed=1234, pin=False):
     inv_K = np.linalg.pinv(K)
     inputs[("K", 0)] = torch.from_numpy(np.repeat(K[None], B, 0).copy())
     inputs[("inv_K", 0)] = torch.from_numpy(np.repeat(inv_K[None], B, 0).astype(np.float32).copy())
+    if getattr(opt, "use_affine", False):
+        # what datasets/mono_dataset.py:110-162 adds per item: a random rotation + scaled crop, the intrinsics-space
+        # conjugation matrix Rc, the box in original-resolution pixels, and the two validity masks
+        from . import affine as A
+        angle = (torch.rand(B, 1, generator=g) * 2 - 1) * 10.0
+        ratio = 1.2 + 0.8 * torch.rand(B, 1, generator=g)
+        boxes, Rcs = [], []
+        for b in range(B):
+            r, a = float(ratio[b, 0]), float(angle[b, 0])
+            Hre, Wre = int(H * r), int(W * r)
+            w0, h0 = int((Wre - W) * float(torch.rand(1, generator=g))), int((Hre - H) * float(torch.rand(1, generator=g)))
+            fs = 1 / r
+            R = torch.tensor([[np.cos(-np.pi / 180 * a), np.sin(np.pi / 180 * a), 0],
+                              [np.sin(-np.pi / 180 * a), np.cos(-np.pi / 180 * a), 0], [0, 0, 1]]).float()
+            tmp = R @ torch.tensor([-fs * Wre / 2, -fs * Hre / 2, fs - 1]) + torch.tensor([(Wre / 2 - w0) * fs, (Hre / 2 - h0) * fs, 0])
+            K3, iK3 = inputs[("K", 0)][b, :3, :3], inputs[("inv_K", 0)][b, :3, :3]
+            Rc = iK3 @ R @ K3
+            Rc[:, 2] += iK3 @ tmp
+            Rcs.append(Rc)
+            boxes.append([round(w0 / r), round(h0 / r), round(W / r), round(H / r)])
+        inputs["Rc"], inputs["ratio_local"], inputs["angle"] = torch.stack(Rcs), ratio, angle
+        inputs["box"] = torch.tensor(boxes)
+        ones = torch.ones(B, 1, H, W)
+        rec = (A.affine_transform(ones, angle, inputs["box"]) > 0).float()
+        inputs["valid_mask_rec"] = rec
+        inputs["valid_mask_cons"] = (A.depth_restore(rec, angle, inputs["box"], torch.ones(B, 1)) > 0).float()
+        for f in (-1, 0, 1):
+            inputs[("color_affine", f, 0)] = A.affine_transform(inputs[("color", f, 0)], angle, inputs["box"])
+        inputs[("color_affine_aug", 0, 0)] = A.affine_transform(inputs[("color_aug", 0, 0)], angle, inputs["box"])
     if pin:
         inputs = {k: v.pin_memory() for k, v in inputs.items()}
     if device is not None:

@@ -1,4 +1,4 @@
-"""Golden losses of the reference's own Trainer.process_batch (train.py:698-885, no affine branch) on CPU for seeded
+"""Golden losses of the reference's own Trainer.process_batch (train.py:698-885, without and with the affine branch) on CPU for seeded
 inputs and name-keyed weights (run in the build container only).  Writes tests/golden/step_golden.json, consumed by
 tests/test_trainstep_cuda.py::test_multi_frame_step_matches_reference."""
 import copy
@@ -9,6 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(HERE))
+sys.path.append(os.path.dirname(os.path.dirname(HERE)))  # repo root: mono_vifi_b200.affine builds the affine INPUTS
 import ref_harness  # noqa: E402
 import net_fill  # noqa: E402
 
@@ -30,9 +31,14 @@ def inputs_for(B, H, W):
     return inp
 
 
+import affine_inputs  # noqa: E402
+
 out = {"B": B, "H": H, "W": W}
-for backbone in ("ResNet18", "DHRNet"):
+for backbone in ("ResNet18", "DHRNet", "ResNet18_affine"):
+    use_affine = backbone.endswith("_affine")     # the same step with the affine-augmentation branch (train.py:815-883)
+    key, backbone = backbone, backbone.split("_")[0]
     tr = ref_harness.make_trainer(T, B, H, W)
+    tr.opt.use_affine = use_affine
     tr.opt.backbone = backbone
     tr.opt.fuse_model_type = "shared_encoder"
     torch.manual_seed(0)
@@ -56,7 +62,10 @@ for backbone in ("ResNet18", "DHRNet"):
     tr.models = m
     tr.model_vfi_train = net_fill.fill_(networks.IFRNet("small"), scale=0.7).eval()
     torch.manual_seed(1)
-    _, losses = tr.process_batch(inputs_for(B, H, W))
-    out[backbone] = {k: float(v) for k, v in losses.items()}
-    print(backbone, out[backbone])
+    inp = inputs_for(B, H, W)
+    if use_affine:
+        affine_inputs.add_affine_inputs(inp, B, H, W)
+    _, losses = tr.process_batch(inp)
+    out[key] = {k: float(v) for k, v in losses.items()}
+    print(key, out[key])
 json.dump(out, open(os.path.join(HERE, "step_golden.json"), "w"), indent=1, sort_keys=True)

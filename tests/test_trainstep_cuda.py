@@ -151,6 +151,51 @@ def test_multi_frame_step_matches_reference(backbone, backend):
         conv.set_backend("tcgen05")
 
 
+@pytest.mark.parametrize("backend", ["cudnn", "tcgen05"])
+def test_multi_frame_step_with_affine_branch_matches_reference(backend):
+    """process_batch WITH the affine-augmentation branch (train.py:815-883: three more loss groups masked by
+    valid_mask_rec with Rc-conjugated poses, three scale-aware depth-consistency terms through the batched
+    rotate / crop / resize transforms of affine.py) against the unmodified reference's CPU losses
+    (tests/golden/step_golden.json["ResNet18_affine"], inputs from tests/affine_inputs.py)."""
+    import json
+    import os
+    import torch
+    import affine_inputs
+    import net_fill
+    from mono_vifi_b200 import conv, networks as N, trainer as TR
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_golden.json")))
+    B, H, W = gold["B"], gold["H"], gold["W"]
+    dev = torch.device("cuda:0")
+    conv.set_backend(backend)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        opt = TR.Options(batch_size=B, height=H, width=W, backbone="ResNet18", multi_frame=True, fuse_model_type="shared_encoder",
+                         use_affine=True)
+        torch.manual_seed(0)
+        models = TR.build_models(opt, torch.device("cpu"))
+        for name, mod in models.items():
+            if name == "encoder_mf":
+                continue
+            net_fill.fill_(mod, scale=0.5 if name != "depth_mf" else 0.6)
+        vfi = net_fill.fill_(N.IFRNet("small"), scale=0.7).eval().to(dev)
+        for mod in models.values():
+            mod.to(dev).train()
+        inputs = affine_inputs.add_affine_inputs(_golden_inputs(B, H, W, dev), B, H, W)
+        torch.manual_seed(1)
+        out = TR.multi_frame_losses(models, vfi, inputs, opt)
+        out["loss"].backward()
+        tol = 2e-3 if backend == "cudnn" else 2e-2   # fp32 vs the TF32 tensor-core path through ~40 layers
+        g = gold["ResNet18_affine"]
+        assert abs(float(out["loss_base"]) - g["loss_base"]) <= tol * g["loss_base"], (float(out["loss_base"]), g["loss_base"])
+        assert abs(float(out["loss_dc"]) - g["loss_dc"]) <= 5 * tol * g["loss_dc"] + 1e-5, (float(out["loss_dc"]), g["loss_dc"])
+        grads = [p.grad for m in models.values() for p in m.parameters() if p.grad is not None]
+        assert len(grads) > 50 and all(torch.isfinite(gr).all() for gr in grads)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+        conv.set_backend("tcgen05")
+
+
 def test_multi_frame_train_step_litemono_runs():
     """Lite-Mono backbone (depth-wise / dilated convolutions go to the library path and are counted) + fusion + IFRNet_S
     through TrainStep: finite, decreasing loss."""
