@@ -350,7 +350,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32 (tf32 tensor-core convolutions, as torch's cuDNN default)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": args.batch, "global_batch": args.batch * world,
                        "height": args.height, "width": args.width, "parallelism": "dp%d" % world,
-                       "launch": graph_note, "streams": "pose branch on a second stream, concurrent with the depth branch" if step.side is not None else "one stream",
+                       "launch": graph_note, "streams": ("pose passes on side streams concurrent with the depth branch, weight gradients on companion streams"
+                                   if step.side is not None else "one stream"),
                        "optimizer": "torch clip_grad_norm_ + AdamW" if args.torch_optimizer else "fused clip + AdamW over flat arenas (mvf_adamw_step)",
                        "conv_backend": conv.get_backend(), "conv_calls_per_step": conv_calls,
                        "conv_kernel_launches_per_step": conv_launches, "bn_calls_per_step": bn_calls,
