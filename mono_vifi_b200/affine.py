@@ -132,3 +132,34 @@ def conjugate_pose(pose, Rc):
     out[:, :3, :3] = torch.matmul(Rc, torch.matmul(pose[:, :3, :3], torch.linalg.inv_ex(Rc)[0]))
     out[:, :3, 3:4] = torch.matmul(Rc, pose[:, :3, 3:4])
     return out
+
+
+def augmentation_geometry(K, inv_K, angle, ratio, origin, H, W):
+    """What the data loader derives for one affine augmentation (datasets/mono_dataset.py:110-136), for a whole batch:
+    the image is enlarged by `ratio` (> 1), rotated by `angle` degrees about its centre and an H x W window is cut at
+    `origin` (fractions in [0,1) of the slack in x and y).  Returns
+      Rc   [B,3,3]  camera-space matrix with  p_aug ~ K Rc K^-1 p  (rotation R in the image plane conjugated by K, plus the
+                    crop / scale offset folded into the third column),
+      box  [B,4]    the window (x0, y0, w, h) in ORIGINAL-resolution pixels, i.e. divided by ratio and rounded.
+    K / inv_K [B,4,4] (or [B,3,3]), angle / ratio [B] or [B,1], origin [B,2]."""
+    B = angle.shape[0]
+    angle, ratio = angle.reshape(B).double(), ratio.reshape(B).double()
+    K3, iK3 = K[:, :3, :3].float().cpu(), inv_K[:, :3, :3].float().cpu()
+    He, We = (H * ratio).floor(), (W * ratio).floor()                      # enlarged size, truncated like int()
+    w0 = ((We - W) * origin[:, 0].double()).floor()
+    h0 = ((He - H) * origin[:, 1].double()).floor()
+    rad = angle * (math.pi / 180.0)
+    c, s_ = torch.cos(rad), torch.sin(rad)
+    R = torch.zeros(B, 3, 3, dtype=torch.float64)
+    R[:, 0, 0], R[:, 0, 1], R[:, 1, 0], R[:, 1, 1], R[:, 2, 2] = c, s_, -s_, c, 1.0
+    R = R.float()
+    fs = 1.0 / ratio
+    centre = torch.stack([-fs * We / 2, -fs * He / 2, fs - 1], 1).float()
+    shift = torch.stack([(We / 2 - w0) * fs, (He / 2 - h0) * fs, torch.zeros(B, dtype=torch.float64)], 1).float()
+    offset = torch.bmm(R, centre[:, :, None])[:, :, 0] + shift
+    Rc = torch.bmm(torch.bmm(iK3, R), K3)
+    Rc[:, :, 2] += torch.bmm(iK3, offset[:, :, None])[:, :, 0]
+    rnd = lambda v: torch.round(v).long()                                   # Python round(): half to even, as torch.round
+    box = torch.stack([rnd(w0 / ratio), rnd(h0 / ratio), rnd(W / ratio), rnd(H / ratio)], 1)
+    return Rc, box
+

@@ -408,22 +408,9 @@ def synthetic_inputs(opt, device=None, seed=1234, pin=False):
         from . import affine as A
         angle = (torch.rand(B, 1, generator=g) * 2 - 1) * 10.0
         ratio = 1.2 + 0.8 * torch.rand(B, 1, generator=g)
-        boxes, Rcs = [], []
-        for b in range(B):
-            r, a = float(ratio[b, 0]), float(angle[b, 0])
-            Hre, Wre = int(H * r), int(W * r)
-            w0, h0 = int((Wre - W) * float(torch.rand(1, generator=g))), int((Hre - H) * float(torch.rand(1, generator=g)))
-            fs = 1 / r
-            R = torch.tensor([[np.cos(-np.pi / 180 * a), np.sin(np.pi / 180 * a), 0],
-                              [np.sin(-np.pi / 180 * a), np.cos(-np.pi / 180 * a), 0], [0, 0, 1]]).float()
-            tmp = R @ torch.tensor([-fs * Wre / 2, -fs * Hre / 2, fs - 1]) + torch.tensor([(Wre / 2 - w0) * fs, (Hre / 2 - h0) * fs, 0])
-            K3, iK3 = inputs[("K", 0)][b, :3, :3], inputs[("inv_K", 0)][b, :3, :3]
-            Rc = iK3 @ R @ K3
-            Rc[:, 2] += iK3 @ tmp
-            Rcs.append(Rc)
-            boxes.append([round(w0 / r), round(h0 / r), round(W / r), round(H / r)])
-        inputs["Rc"], inputs["ratio_local"], inputs["angle"] = torch.stack(Rcs), ratio, angle
-        inputs["box"] = torch.tensor(boxes)
+        inputs["Rc"], inputs["box"] = A.augmentation_geometry(inputs[("K", 0)], inputs[("inv_K", 0)], angle, ratio,
+                                                              torch.rand(B, 2, generator=g), H, W)
+        inputs["ratio_local"], inputs["angle"] = ratio, angle
         ones = torch.ones(B, 1, H, W)
         rec = (A.affine_transform(ones, angle, inputs["box"]) > 0).float()
         inputs["valid_mask_rec"] = rec
