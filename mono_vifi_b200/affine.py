@@ -42,7 +42,9 @@ def rotate(img, angle_deg):
     base[..., 0].copy_(torch.linspace(-W * 0.5 + 0.5, W * 0.5 + 0.5 - 1, steps=W, device=dev))
     base[..., 1].copy_(torch.linspace(-H * 0.5 + 0.5, H * 0.5 + 0.5 - 1, steps=H, device=dev).unsqueeze(-1))
     base[..., 2].fill_(1)
-    rescaled = theta.transpose(1, 2) / torch.tensor([0.5 * W, 0.5 * H], dtype=torch.float32, device=dev)
+    # (fill kernels, not a host->device copy: the step may be inside a CUDA-graph capture)
+    half = torch.stack([torch.full((), 0.5 * W, dtype=torch.float32, device=dev), torch.full((), 0.5 * H, dtype=torch.float32, device=dev)])
+    rescaled = theta.transpose(1, 2) / half
     grid = base.view(1, H * W, 3).expand(B, H * W, 3).bmm(rescaled).view(B, H, W, 2)
     return F.grid_sample(img, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
 
