@@ -147,6 +147,19 @@ int mvf_conv2d_supported(const mvf_conv2d_desc* d); /* 1 / 0 (reason in mvf_last
 int mvf_conv2d_forward(const mvf_conv2d_desc* d, const float* x, const float* w_packed, const float* bias /*or NULL*/,
                        float* y, int act, void* stream);
 
+/* Data gradient of a STRIDE-2 convolution (the three down-sampling 3x3 convolutions and 1x1 shortcuts of every ResNet
+ * encoder, networks/monodepth2.py:16-31 via torchvision's BasicBlock): d describes the forward problem, x_stride the
+ * gradient being produced (grad_x [B,Cin,H,W]) and y_stride the incoming one (grad_y [B,Cout,Ho,Wo]); w_packed is the
+ * dgrad = 1 bank.  The input pixels split into four parity classes, each a small stride-1 convolution over grad_y that
+ * lands on a stride-2 lattice of grad_x; classes without taps (1x1: three of four) are not written -- pass a zeroed
+ * grad_x when KH or KW is 1.  mvf_conv2d_dgrad_s2_plan writes the class / tap table the kernel walks (n_classes, then
+ * per class py, px, ntaps and ntaps x (dy, dx, packed tap index)) and returns the number of ints; it runs on the host.
+ * Status: written at the end of round 1 behind MVF_DGRAD_S2=1 in the Python binding; the plan is checked on the CPU
+ * (tests/test_dgrad_s2_plan.py), the kernel has not been run on hardware yet. */
+int mvf_conv2d_dgrad_s2_supported(const mvf_conv2d_desc* d);
+int mvf_conv2d_dgrad_s2(const mvf_conv2d_desc* d, const float* grad_y, const float* w_packed, float* grad_x, void* stream);
+int mvf_conv2d_dgrad_s2_plan(int KH, int KW, int pad, int* table, int capacity);
+
 /* weight gradient: grad_w[Cout,Cin,KH,KW] (contiguous, the parameter's layout) = sum over output pixels of
  * grad_out (x) input patches; d->x_stride describes x, d->y_stride describes grad_out (both channels-last).
  * Split-K partial sums go to `workspace` (mvf_conv2d_wgrad_workspace_floats(d) floats, caller-owned scratch) and are

@@ -61,6 +61,9 @@ SIGNATURES = {
     "mvf_bn_relu_bwd": (_i, [_vp] * 11 + [_sz, ctypes.c_longlong, _i, _i, _vp]),
     "mvf_act_bwd_bias": (_i, [_vp] * 5 + [_sz, ctypes.c_longlong, _i, _i, _vp]),
     "mvf_stream_capture_id": (ctypes.c_ulonglong, [_vp]),
+    "mvf_conv2d_dgrad_s2_supported": (_i, [_CD]),
+    "mvf_conv2d_dgrad_s2": (_i, [_CD, _vp, _vp, _vp, _vp]),
+    "mvf_conv2d_dgrad_s2_plan": (_i, [_i, _i, _i, ctypes.POINTER(ctypes.c_int), _i]),
     "mvf_adamw_workspace_bytes": (_sz, []),
     "mvf_adamw_step": (_i, [_vp, _vp, _vp, _vp, ctypes.c_longlong, _vp, _vp, _sz, _f, _f, _f, _f, _f, _f, _vp]),
     "mvf_gather_grads": (_i, [_vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_longlong),

@@ -230,6 +230,8 @@ class _Conv2dTC(torch.autograd.Function):
                     gx = conv_forward_raw(gyd, pack_filters(wd, dgrad=True), None, Cin, KH, KW, KH - 1 - pad)
                 finally:
                     _tag = "fprop"
+            elif dgrad_s2_enabled and _pair(stride) == (2, 2) and Cout % 4 == 0 and Cin % 4 == 0 and KH <= 8 and KW <= 8:
+                gx = input_grad_s2(x, gy, weight, pad)
             else:
                 gx = input_grad_library(x, gy, weight, pad, stride)
         if fork is not None:
@@ -239,6 +241,28 @@ class _Conv2dTC(torch.autograd.Function):
         if want_gb:
             gb = gy.sum((0, 2, 3))
         return gx, gw, gb, None, None, None
+
+
+# Stride-2 data gradient on the tcgen05 path (mvf_conv2d_dgrad_s2): written at the end of round 1, its class / tap plan is
+# checked on the CPU (tests/test_dgrad_s2_plan.py) but the kernel has not been run on hardware, so it is opt-in.
+dgrad_s2_enabled = os.environ.get("MVF_DGRAD_S2", "0") == "1"
+
+
+def input_grad_s2(x, gy, weight, pad):
+    """dL/dx of a stride-2 convolution: four parity classes, each a small stride-1 convolution over gy (one launch)"""
+    Cout, Cin, KH, KW = weight.shape
+    B, _, H, W = x.shape
+    gy = _as_input(gy)
+    # classes without taps are not written by the kernel (1 x k / k x 1 filters): start from zeros then
+    alloc = torch.zeros if (KH == 1 or KW == 1) else torch.empty
+    gx = alloc(B, H, W, Cin, device=gy.device, dtype=torch.float32).permute(0, 3, 1, 2)
+    d = _desc(B, Cin, H, W, Cout, KH, KW, pad, 2, gx, gy)
+    launches["dgrad"] += 1
+    Ho, Wo = gy.shape[2], gy.shape[3]
+    flops = 2.0 * B * Ho * Wo * Cout * Cin * KH * KW
+    _lib.check(_timed("dgrad", flops, lambda: _lib.lib().mvf_conv2d_dgrad_s2(d, gy.data_ptr(), pack_filters(weight, dgrad=True).data_ptr(),
+                                                                            gx.data_ptr(), _stream(gy))), "mvf_conv2d_dgrad_s2")
+    return gx
 
 
 def input_grad_library(x, gy, weight, pad, stride):

@@ -262,6 +262,26 @@ int mvf_conv2d_forward(const mvf_conv2d_desc* d, const float* x, const float* w_
     if (e != cudaSuccess) return why ? fail(MVF_ERR_CUDA, why) : fail(MVF_ERR_CUDA, "mvf_conv2d_forward launch", e);
     return MVF_OK;
 }
+int mvf_conv2d_dgrad_s2_supported(const mvf_conv2d_desc* d) {
+    if (!d) return 0;
+    const char* why = mvf::tc::conv_dgrad_s2_check(to_desc(d));
+    if (why) {
+        fail(MVF_ERR_INVALID, why);
+        return 0;
+    }
+    return 1;
+}
+int mvf_conv2d_dgrad_s2(const mvf_conv2d_desc* d, const float* grad_y, const float* w_packed, float* grad_x, void* stream) {
+    if (!d || !grad_y || !w_packed || !grad_x) return fail(MVF_ERR_INVALID, "mvf_conv2d_dgrad_s2: null pointer");
+    const char* why = nullptr;
+    cudaError_t e = mvf::tc::conv_dgrad_s2(to_desc(d), grad_y, w_packed, grad_x, (cudaStream_t)stream, &why);
+    if (e != cudaSuccess) return why ? fail(e == cudaErrorInvalidValue ? MVF_ERR_INVALID : MVF_ERR_CUDA, why) : fail(MVF_ERR_CUDA, "mvf_conv2d_dgrad_s2 launch", e);
+    return MVF_OK;
+}
+int mvf_conv2d_dgrad_s2_plan(int KH, int KW, int pad, int* table, int capacity) {
+    if (!table || capacity <= 0 || KH <= 0 || KW <= 0 || KH > 8 || KW > 8 || pad < 0) return -1;
+    return mvf::tc::conv_dgrad_s2_plan_table(KH, KW, pad, table, capacity);
+}
 static mvf::tc::WgradDesc to_wdesc(const mvf_conv2d_desc* d) {
     mvf::tc::WgradDesc c;
     c.B = d->B; c.Cin = d->Cin; c.H = d->H; c.W = d->W; c.Cout = d->Cout; c.KH = d->KH; c.KW = d->KW; c.pad = d->pad;

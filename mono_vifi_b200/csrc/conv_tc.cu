@@ -372,6 +372,190 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_persistent_kernel(const _
 }
 
 
+// ---- data gradient of a stride-2 convolution (MVF_DGRAD_S2=1; written at the end of round 1, NOT yet run on hardware) ---
+// gx[iy, ix, ci] = sum over (kh, kw, co) with iy = 2*oy + kh - pad, ix = 2*ox + kw - pad of gy[oy, ox, co] * w[co, ci, kh, kw].
+// The input pixels fall into four parity classes (py, px) = (iy & 1, ix & 1); within a class only the taps with
+// kh = py + pad (mod 2), kw = px + pad (mod 2) contribute and pixel (2i + py, 2j + px) reads gy at (i + dy, j + dx) with
+// dy = (py + pad - kh) / 2: every class is a small stride-1 convolution over gy (<= 4 taps for 3x3, 1 for 1x1) whose
+// output lands on a stride-2 lattice of gx.  One persistent launch walks the tiles of all non-empty classes with the
+// skeleton of conv_igemm_persistent_kernel; gy boxes that leave the image are zero-filled by TMA.  Classes without taps
+// (1x1 stride 2: three of four) are not visited -- the caller provides a zeroed gx in that case.
+struct S2Class {
+    int py, px, ntaps;
+    int dy[16], dx[16], tap[16];  // tap = index into the dgrad-packed (flipped) bank: (KH-1-kh) * KW + (KW-1-kw)
+};
+struct S2Plan {
+    int n;  // non-empty classes
+    S2Class c[4];
+};
+
+S2Plan plan_dgrad_s2(int KH, int KW, int pad) {
+    S2Plan pl = {};
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            S2Class c = {};
+            c.py = py;
+            c.px = px;
+            for (int kh = 0; kh < KH; ++kh) {
+                if ((py + pad - kh) & 1) continue;
+                for (int kw = 0; kw < KW; ++kw) {
+                    if ((px + pad - kw) & 1) continue;
+                    if (c.ntaps >= 16) continue;  // callers check conv_dgrad_s2_check first
+                    c.dy[c.ntaps] = (py + pad - kh) / 2;  // exact: the numerator is even
+                    c.dx[c.ntaps] = (px + pad - kw) / 2;
+                    c.tap[c.ntaps] = (KH - 1 - kh) * KW + (KW - 1 - kw);
+                    ++c.ntaps;
+                }
+            }
+            if (c.ntaps > 0) pl.c[pl.n++] = c;
+        }
+    return pl;
+}
+
+template <int N_TILE>
+__global__ void __launch_bounds__(NTHREADS) conv_dgrad_s2_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                 const __grid_constant__ CUtensorMap mapB, const ConvArgs p,
+                                                                 const __grid_constant__ S2Plan plan, const int n_mtiles,
+                                                                 const int n_ntiles) {
+    using C = Cfg<N_TILE>;
+    constexpr int TMEM_COLS = (2 * N_TILE) < 32 ? 32 : (2 * N_TILE);
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smA = smem;
+    unsigned char* smB = smem + C::STAGES * A_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smB + C::STAGES * C::B_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + C::STAGES;
+    uint64_t* acc_full = empty_bar + C::STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int TW = 1 << p.tw_log2, TH = TILE_M >> p.tw_log2;
+    const int per_class = n_mtiles * n_ntiles, n_tiles = per_class * plan.n;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+    pdl_sync();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0, ph = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int ci = t / per_class, rem = t - ci * per_class;
+                const S2Class& cl = plan.c[ci];
+                const int m = rem % n_mtiles, nt = rem / n_mtiles;
+                const int tx = m % p.tiles_x, ty = (m / p.tiles_x) % p.tiles_y, b = m / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * TW, y0 = ty * TH, n0 = nt * N_TILE;
+                for (int tp = 0; tp < cl.ntaps; ++tp)
+                    for (int cb = 0; cb < p.n_cblk; ++cb) {
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
+                        // A: gy as (co, ox, oy, b), box (32, TW, TH, 1) at the class's tile origin shifted by the tap
+                        tma_load_4d(smA + s * A_STAGE_BYTES, &mapA, &full_bar[s], cb * BLOCK_K, x0 + cl.dx[tp], y0 + cl.dy[tp], b);
+                        tma_load_3d(smB + s * C::B_STAGE_BYTES, &mapB, &full_bar[s], 0, n0, cl.tap[tp] * p.n_cblk + cb);
+                        if (++s == C::STAGES) { s = 0; ph ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc_tf32(TILE_M, N_TILE, 0, 0);
+        const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
+        int s = 0, ph = 0, acc = 0, accph = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int n_iters = plan.c[t / per_class].ntaps * p.n_cblk;
+            mbar_wait(&acc_empty[acc], accph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_d + (uint32_t)(acc * N_TILE);
+            for (int it = 0; it < n_iters; ++it) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_base = smA_u + (uint32_t)(s * A_STAGE_BYTES), b_base = smB_u + (uint32_t)(s * C::B_STAGE_BYTES);
+#pragma unroll
+                    for (int kg = 0; kg < KGROUPS; ++kg) {
+                        const uint64_t adesc = make_smem_desc(a_base + kg * 32, 16, 1024, SWZ_128B);
+                        const uint64_t bdesc = make_smem_desc(b_base + kg * 32, 16, 1024, SWZ_128B);
+                        umma_tf32(d_tmem, adesc, bdesc, idesc, (it > 0 || kg > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                __syncwarp();
+                if (++s == C::STAGES) { s = 0; ph ^= 1; }
+            }
+            if (elect_one()) umma_commit(&acc_full[acc]);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; accph ^= 1; }
+        }
+    } else {
+        const int q = warp & 3;
+        const int mrow = q * 32 + lane;
+        constexpr int CH = (N_TILE >= 32) ? 32 : 16;
+        int acc = 0, accph = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int ci = t / per_class, rem = t - ci * per_class;
+            const int m = rem % n_mtiles, nt = rem / n_mtiles;
+            const int tx = m % p.tiles_x, ty = (m / p.tiles_x) % p.tiles_y, b = m / (p.tiles_x * p.tiles_y);
+            const int n0 = nt * N_TILE;
+            // tile pixel (i, j) of the class lattice -> input pixel (2i + py, 2j + px)
+            const int iy = 2 * (ty * TH + (mrow >> p.tw_log2)) + plan.c[ci].py, ix = 2 * (tx * TW + (mrow & (TW - 1))) + plan.c[ci].px;
+            const bool pix_ok = (iy < p.Ho) && (ix < p.Wo);
+            float* ypix = p.y + (long long)b * p.y_sB + (long long)iy * p.y_sH + (long long)ix * p.y_sW;
+            const bool vec_ok = ((p.Cout & 3) == 0) && ((reinterpret_cast<uintptr_t>(ypix) & 15) == 0);
+            mbar_wait(&acc_full[acc], accph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < N_TILE; c0 += CH) {
+                uint32_t r[CH];
+                const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N_TILE + c0);
+                if constexpr (CH == 32) tmem_ld32(taddr, r);
+                else tmem_ld16(taddr, r);
+                tmem_ld_wait();
+                if (!pix_ok || n0 + c0 >= p.Cout) continue;
+                if (vec_ok) {
+#pragma unroll
+                    for (int j = 0; j < CH; j += 4)
+                        if (n0 + c0 + j < p.Cout)
+                            *reinterpret_cast<float4*>(ypix + n0 + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                                        __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j)
+                        if (n0 + c0 + j < p.Cout) ypix[n0 + c0 + j] = __uint_as_float(r[j]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);
+            if (++acc == 2) { acc = 0; accph ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_d, TMEM_COLS);
+    }
+}
+
+
 // ---- stride-1 multi-tap convolutions: one haloed input patch per 32-channel block serves all taps -----------------
 // The per-tap kernel above pulls a fresh 16 KB A tile through L2 for every tap; here the producer loads, once per
 // 32-channel block, the patch of R input rows x P input columns that all KH*KW taps of the CTA's outputs read
@@ -948,6 +1132,128 @@ cudaError_t conv_forward(const ConvDesc& d, const float* x, const float* w_packe
         case 32: return launch<32>(mapA, mapB, a, d.B, st);
         case 64: return launch<64>(mapA, mapB, a, d.B, st);
         default: return launch<128>(mapA, mapB, a, d.B, st);
+    }
+}
+
+
+// ---- host side of the stride-2 data gradient ------------------------------------------------------------------------
+// d describes the FORWARD convolution: x_* = the gradient being produced (gx, [B, Cin, H, W]), y_* = the incoming
+// gradient (gy, [B, Cout, Ho, Wo]); w_packed = mvf_conv2d_pack_filters(.., dgrad = 1) of the forward weights.
+const char* conv_dgrad_s2_check(const ConvDesc& d) {
+    if (d.stride != 2 || d.stride_x != 2) return "strides must be 2";
+    if (d.KH > 8 || d.KW > 8) return "filter larger than 8x8";
+    if (d.Cin % 4 != 0) return "Cin must be a multiple of 4 (16-byte pixels of the produced gradient)";
+    if (d.Cout % 4 != 0) return "Cout must be a multiple of 4 (16-byte pixels of the incoming gradient)";
+    if (d.x_sW % 4 || d.x_sH % 4 || d.x_sB % 4 || d.y_sW % 4 || d.y_sH % 4 || d.y_sB % 4) return "strides must be multiples of 4 elements";
+    return nullptr;
+}
+
+int conv_dgrad_s2_plan_table(int KH, int KW, int pad, int* out, int capacity) {
+    // flat copy of the plan for tests: n, then per class: py, px, ntaps, ntaps x (dy, dx, tap)
+    const S2Plan pl = plan_dgrad_s2(KH, KW, pad);
+    int k = 0;
+    auto put = [&](int v) { if (k < capacity) out[k] = v; ++k; };
+    put(pl.n);
+    for (int i = 0; i < pl.n; ++i) {
+        put(pl.c[i].py); put(pl.c[i].px); put(pl.c[i].ntaps);
+        for (int t = 0; t < pl.c[i].ntaps; ++t) { put(pl.c[i].dy[t]); put(pl.c[i].dx[t]); put(pl.c[i].tap[t]); }
+    }
+    return k;
+}
+
+template <int N_TILE>
+static cudaError_t launch_dgrad_s2(const CUtensorMap& mapA, const CUtensorMap& mapB, const ConvArgs& a, const S2Plan& plan, int n_mtiles,
+                                   int n_ntiles, cudaStream_t st) {
+    using C = Cfg<N_TILE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_dgrad_s2_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int n_tiles = n_mtiles * n_ntiles * plan.n;
+    const int per_sm = (C::SMEM_BYTES <= 110 * 1024 && 2 * N_TILE * 2 <= 512) ? 2 : 1;
+    const int ctas = n_tiles < per_sm * n_sm ? n_tiles : per_sm * n_sm;
+    return launch_pdl(conv_dgrad_s2_kernel<N_TILE>, dim3(ctas), dim3(NTHREADS), C::SMEM_BYTES, st, mapA, mapB, a, plan, n_mtiles, n_ntiles);
+}
+
+cudaError_t conv_dgrad_s2(const ConvDesc& d, const float* gy, const float* w_packed, float* gx, cudaStream_t st, const char** why) {
+    *why = conv_dgrad_s2_check(d);
+    if (*why) return cudaErrorInvalidValue;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) {
+        *why = "cuTensorMapEncodeTiled is not available from the driver";
+        return cudaErrorNotSupported;
+    }
+    if (((uintptr_t)gy & 15) || ((uintptr_t)w_packed & 15) || ((uintptr_t)gx & 15)) {
+        *why = "pointers must be 16-byte aligned";
+        return cudaErrorInvalidValue;
+    }
+    const int Ho = out_size(d.H, d.KH, d.pad, 2), Wo = out_size(d.W, d.KW, d.pad, 2);
+    const S2Plan plan = plan_dgrad_s2(d.KH, d.KW, d.pad);
+    if (plan.n == 0) return cudaSuccess;
+    const int Hc = (d.H + 1) / 2, Wc = (d.W + 1) / 2;  // lattice of the largest class
+    ConvArgs a = {};
+    a.y = gx;
+    a.bias = nullptr;
+    a.y_sB = d.x_sB; a.y_sH = d.x_sH; a.y_sW = d.x_sW;
+    a.Cout = d.Cin; a.Ho = d.H; a.Wo = d.W;
+    a.KH = d.KH; a.KW = d.KW; a.pad = d.pad; a.stride = 1; a.stride_x = 1;
+    int best = 5;
+    long long best_cost = -1;
+    for (int j = 7; j >= 1; --j) {
+        const int tw = 1 << j, th = TILE_M >> j;
+        const long long cost = (long long)((Wc + tw - 1) / tw) * ((Hc + th - 1) / th);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = j;
+        }
+    }
+    a.tw_log2 = best;
+    const int TW = 1 << best, TH = TILE_M >> best;
+    a.tiles_x = (Wc + TW - 1) / TW;
+    a.tiles_y = (Hc + TH - 1) / TH;
+    a.n_cblk = (d.Cout + BLOCK_K - 1) / BLOCK_K;  // K = the forward convolution's output channels
+    a.act = 0;
+    a.dbg = nullptr;
+    int n_tile = 16;
+    while (n_tile < d.Cin && n_tile < 128) n_tile *= 2;
+    CUtensorMap mapA, mapB;
+    {   // gy as (co, ox, oy, b)
+        cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)d.y_sW * 4, (cuuint64_t)d.y_sH * 4, (cuuint64_t)d.y_sB * 4};
+        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(gy), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            *why = "cuTensorMapEncodeTiled failed for the incoming gradient";
+            return cudaErrorInvalidValue;
+        }
+    }
+    {   // dgrad-packed bank as (32 k, Cin, taps * n_cblk)
+        cuuint64_t dims[3] = {BLOCK_K, (cuuint64_t)d.Cin, (cuuint64_t)(d.KH * d.KW * a.n_cblk)};
+        cuuint64_t strides[2] = {BLOCK_K * 4, (cuuint64_t)d.Cin * BLOCK_K * 4};
+        cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)n_tile, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w_packed), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            *why = "cuTensorMapEncodeTiled failed for the packed filter bank";
+            return cudaErrorInvalidValue;
+        }
+    }
+    const int n_mtiles = d.B * a.tiles_x * a.tiles_y, n_ntiles = (d.Cin + n_tile - 1) / n_tile;
+    switch (n_tile) {
+        case 16: return launch_dgrad_s2<16>(mapA, mapB, a, plan, n_mtiles, n_ntiles, st);
+        case 32: return launch_dgrad_s2<32>(mapA, mapB, a, plan, n_mtiles, n_ntiles, st);
+        case 64: return launch_dgrad_s2<64>(mapA, mapB, a, plan, n_mtiles, n_ntiles, st);
+        default: return launch_dgrad_s2<128>(mapA, mapB, a, plan, n_mtiles, n_ntiles, st);
     }
 }
 

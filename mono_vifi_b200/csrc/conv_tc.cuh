@@ -35,6 +35,10 @@ void set_debug_buffer(float* p);  // development aid: dump of pipeline stage 0, 
 const char* conv_check(const ConvDesc& d);  // nullptr if the tcgen05 path covers the problem, else the reason
 cudaError_t conv_forward(const ConvDesc& d, const float* x, const float* w_packed, const float* bias, float* y, int act,
                          cudaStream_t st, const char** why);
+// data gradient of a stride-2 convolution (d = the forward problem: x_* describe gx, y_* describe gy); see conv_tc.cu
+const char* conv_dgrad_s2_check(const ConvDesc& d);
+cudaError_t conv_dgrad_s2(const ConvDesc& d, const float* gy, const float* w_packed, float* gx, cudaStream_t st, const char** why);
+int conv_dgrad_s2_plan_table(int KH, int KW, int pad, int* out, int capacity);
 
 }  // namespace tc
 }  // namespace mvf
