@@ -243,9 +243,10 @@ class _Conv2dTC(torch.autograd.Function):
         return gx, gw, gb, None, None, None
 
 
-# Stride-2 data gradient on the tcgen05 path (mvf_conv2d_dgrad_s2): written at the end of round 1, its class / tap plan is
-# checked on the CPU (tests/test_dgrad_s2_plan.py) but the kernel has not been run on hardware, so it is opt-in.
-dgrad_s2_enabled = os.environ.get("MVF_DGRAD_S2", "0") == "1"
+# Stride-2 data gradient on the tcgen05 path (mvf_conv2d_dgrad_s2): class / tap plan checked on the CPU
+# (tests/test_dgrad_s2_plan.py), kernel against fp64 torch on the GPU (tests/test_conv_tc_cuda.py).  MVF_DGRAD_S2=0 routes these
+# gradients to cuDNN for A/B timing; they are then counted in conv.stats["cudnn_dgrad"].
+dgrad_s2_enabled = os.environ.get("MVF_DGRAD_S2", "1") == "1"
 
 
 def input_grad_s2(x, gy, weight, pad):

@@ -221,164 +221,13 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
 }
 
 
-// ---- persistent variant of the per-tap kernel (MVF_CONV_IGEMM_PERSISTENT=1; passes the conv parity tests, NOT yet timed) ---
-// conv_igemm_kernel runs ONE 128-pixel tile per CTA: the stem launches 2880 of them and each pays barrier
-// initialisation, TMEM allocation, a cold pipeline fill and an un-overlapped epilogue (118 us measured against a ~20 us
-// MMA / HBM bound).  Here min(tiles, resident CTAs) CTAs walk the tiles: the producer's stage ring runs ahead across
-// tile boundaries and the accumulator is double-buffered in TMEM so that the epilogue of tile i overlaps the MMAs of
-// tile i + 1 -- the same skeleton as conv_patch_kernel below, with the per-tap A boxes of this kernel.
-template <int N_TILE>
-__global__ void __launch_bounds__(NTHREADS) conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                         const __grid_constant__ CUtensorMap mapB, const ConvArgs p,
-                                                                         const int n_mtiles, const int n_tiles) {
-    using C = Cfg<N_TILE>;
-    constexpr int TMEM_COLS = (2 * N_TILE) < 32 ? 32 : (2 * N_TILE);
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* smA = smem;
-    unsigned char* smB = smem + C::STAGES * A_STAGE_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smB + C::STAGES * C::B_STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + C::STAGES;
-    uint64_t* acc_full = empty_bar + C::STAGES;
-    uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int TW = 1 << p.tw_log2, TH = TILE_M >> p.tw_log2;
-    const int n_iters = p.KH * p.KW * p.n_cblk;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&mapA);
-        tma_prefetch_desc(&mapB);
-        for (int s = 0; s < C::STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 128);  // every epilogue thread arrives
-        }
-        fence_barrier_init();
-    }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_d = *tmem_slot;
-    pdl_sync();
-
-    if (warp == 0) {
-        // ===== TMA producer: one continuous stage sequence over all of this CTA's tiles =====
-        if (lane == 0) {
-            int s = 0, ph = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int m = t % n_mtiles, nt = t / n_mtiles;
-                const int tx = m % p.tiles_x, ty = (m / p.tiles_x) % p.tiles_y, b = m / (p.tiles_x * p.tiles_y);
-                const int x0 = tx * TW, y0 = ty * TH, n0 = nt * N_TILE;
-                int kh = 0, kw = 0, cb = 0;  // it = (kh * KW + kw) * n_cblk + cb
-                for (int it = 0; it < n_iters; ++it) {
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
-                    tma_load_4d(smA + s * A_STAGE_BYTES, &mapA, &full_bar[s], cb * BLOCK_K, x0 * p.stride_x + kw - p.pad,
-                                y0 * p.stride + kh - p.pad, b);
-                    tma_load_3d(smB + s * C::B_STAGE_BYTES, &mapB, &full_bar[s], 0, n0, it);
-                    if (++s == C::STAGES) { s = 0; ph ^= 1; }
-                    if (++cb == p.n_cblk) { cb = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer: whole warp runs the uniform loop, one elected lane issues =====
-        constexpr uint32_t idesc = make_idesc_tf32(TILE_M, N_TILE, 0, 0);
-        const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
-        int s = 0, ph = 0, acc = 0, accph = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            mbar_wait(&acc_empty[acc], accph ^ 1);  // the epilogue has drained this accumulator buffer
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_d + (uint32_t)(acc * N_TILE);
-            for (int it = 0; it < n_iters; ++it) {
-                mbar_wait(&full_bar[s], ph);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t a_base = smA_u + (uint32_t)(s * A_STAGE_BYTES), b_base = smB_u + (uint32_t)(s * C::B_STAGE_BYTES);
-#pragma unroll
-                    for (int kg = 0; kg < KGROUPS; ++kg) {
-                        const uint64_t adesc = make_smem_desc(a_base + kg * 32, 16, 1024, SWZ_128B);
-                        const uint64_t bdesc = make_smem_desc(b_base + kg * 32, 16, 1024, SWZ_128B);
-                        umma_tf32(d_tmem, adesc, bdesc, idesc, (it > 0 || kg > 0) ? 1u : 0u);
-                    }
-                    umma_commit(&empty_bar[s]);
-                }
-                __syncwarp();
-                if (++s == C::STAGES) { s = 0; ph ^= 1; }
-            }
-            if (elect_one()) umma_commit(&acc_full[acc]);
-            __syncwarp();
-            if (++acc == 2) { acc = 0; accph ^= 1; }
-        }
-    } else {
-        // ===== epilogue: warps 2..5 own the TMEM lane quarter (warp % 4); one thread = one output pixel =====
-        const int q = warp & 3;
-        const int mrow = q * 32 + lane;
-        constexpr int CH = (N_TILE >= 32) ? 32 : 16;
-        int acc = 0, accph = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int m = t % n_mtiles, nt = t / n_mtiles;
-            const int tx = m % p.tiles_x, ty = (m / p.tiles_x) % p.tiles_y, b = m / (p.tiles_x * p.tiles_y);
-            const int x0 = tx * TW, y0 = ty * TH, n0 = nt * N_TILE;
-            const int oy = y0 + (mrow >> p.tw_log2), ox = x0 + (mrow & (TW - 1));
-            const bool pix_ok = (oy < p.Ho) && (ox < p.Wo);
-            float* ypix = p.y + (long long)b * p.y_sB + (long long)oy * p.y_sH + (long long)ox * p.y_sW;
-            const bool vec_ok = ((p.Cout & 3) == 0) && ((reinterpret_cast<uintptr_t>(ypix) & 15) == 0);
-            mbar_wait(&acc_full[acc], accph);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < N_TILE; c0 += CH) {
-                uint32_t r[CH];
-                const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N_TILE + c0);
-                if constexpr (CH == 32) tmem_ld32(taddr, r);
-                else tmem_ld16(taddr, r);
-                tmem_ld_wait();
-                if (!pix_ok || n0 + c0 >= p.Cout) continue;
-                float v[CH];
-#pragma unroll
-                for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
-                bias_act<CH>(v, p.bias, n0 + c0, p.Cout, p.act);
-                if (vec_ok) {
-#pragma unroll
-                    for (int j = 0; j < CH; j += 4)
-                        if (n0 + c0 + j < p.Cout)
-                            *reinterpret_cast<float4*>(ypix + n0 + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < CH; ++j)
-                        if (n0 + c0 + j < p.Cout) ypix[n0 + c0 + j] = v[j];
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&acc_empty[acc]);  // this thread's TMEM reads of the buffer are complete
-            if (++acc == 2) { acc = 0; accph ^= 1; }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_d, TMEM_COLS);
-    }
-}
-
-
-// ---- data gradient of a stride-2 convolution (MVF_DGRAD_S2=1; written at the end of round 1, NOT yet run on hardware) ---
+// ---- data gradient of a stride-2 convolution (default since round 2; MVF_DGRAD_S2=0 routes to cuDNN for A/B) ---
 // gx[iy, ix, ci] = sum over (kh, kw, co) with iy = 2*oy + kh - pad, ix = 2*ox + kw - pad of gy[oy, ox, co] * w[co, ci, kh, kw].
 // The input pixels fall into four parity classes (py, px) = (iy & 1, ix & 1); within a class only the taps with
 // kh = py + pad (mod 2), kw = px + pad (mod 2) contribute and pixel (2i + py, 2j + px) reads gy at (i + dy, j + dx) with
 // dy = (py + pad - kh) / 2: every class is a small stride-1 convolution over gy (<= 4 taps for 3x3, 1 for 1x1) whose
 // output lands on a stride-2 lattice of gx.  One persistent launch walks the tiles of all non-empty classes with the
-// skeleton of conv_igemm_persistent_kernel; gy boxes that leave the image are zero-filled by TMA.  Classes without taps
+// skeleton of conv_patch_kernel (persistent tiles, two accumulator buffers in TMEM); gy boxes that leave the image are zero-filled by TMA.  Classes without taps
 // (1x1 stride 2: three of four) are not visited -- the caller provides a zeroed gx in that case.
 struct S2Class {
     int py, px, ntaps;
@@ -867,24 +716,6 @@ cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const ConvA
         attr_set = true;
     }
     dim3 grid(B * a.tiles_x * a.tiles_y, (a.Cout + N_TILE - 1) / N_TILE);
-    static const bool persistent = getenv("MVF_CONV_IGEMM_PERSISTENT") != nullptr && atoi(getenv("MVF_CONV_IGEMM_PERSISTENT")) != 0;
-    if (persistent && N_TILE <= 256) {
-        static bool attr2 = false;
-        if (!attr2) {
-            cudaError_t e = cudaFuncSetAttribute(conv_igemm_persistent_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 C::SMEM_BYTES);
-            if (e != cudaSuccess) return e;
-            attr2 = true;
-        }
-        int dev = 0, n_sm = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        const int n_mtiles = (int)grid.x, n_tiles = (int)(grid.x * grid.y);
-        const int per_sm = (C::SMEM_BYTES <= 110 * 1024 && 2 * N_TILE * 2 <= 512) ? 2 : 1;  // shared memory and TMEM columns
-        const int ctas = n_tiles < per_sm * n_sm ? n_tiles : per_sm * n_sm;
-        return launch_pdl(conv_igemm_persistent_kernel<N_TILE>, dim3(ctas), dim3(NTHREADS), C::SMEM_BYTES, st, mapA, mapB, a,
-                          n_mtiles, n_tiles);
-    }
     return launch_pdl(conv_igemm_kernel<N_TILE>, grid, dim3(NTHREADS), C::SMEM_BYTES, st, mapA, mapB, a);
 }
 

@@ -39,6 +39,10 @@ CASES = {
     "noauto": (16, 2, 24, 40, True, True, (0, 0, 1), True),
     "avg_noauto": (17, 1, 24, 40, True, False, (0, 1, 1), True),
     "cfg1": (1234, 2, 128, 416, True, False, (0, 0, 0), False),
+    # BASELINE.json configs 2-5 at their full sizes (sub-sampled maps, stride 499; full argmin map)
+    "cfg2": (1235, 12, 192, 640, True, False, (0, 0, 0), 499),
+    "cfg4": (1236, 6, 320, 1024, True, True, (0, 0, 0), 499),
+    "cfg5": (1237, 8, 384, 1280, True, False, (0, 0, 0), 499),
 }
 
 
@@ -141,13 +145,13 @@ def run_case(T, name, spec):
         idx=idx.numpy().astype(np.uint8),
         grad_disp_abs_sum=np.float64(disp.grad.abs().double().sum().item()),
     )
-    if full:
+    if full is True:
         out.update(grid=torch.stack(grids).numpy(), x0y0=xy, warp=torch.stack([w.detach() for w in warps]).numpy(),
                    ssim0=ssim0.numpy(), rep=torch.cat(rep, 1).numpy(), idl=torch.cat(idl, 1).numpy(),
                    to_optimise=to_opt.numpy(), grad_disp=disp.grad.numpy(),
                    depth=depth.detach().numpy())
     else:
-        st = 37
+        st = 37 if full is False else int(full)
         out.update(stride=np.int64(st), to_optimise_sub=to_opt.numpy().ravel()[::st].copy(),
                    grad_disp_sub=disp.grad.numpy().ravel()[::st].copy(),
                    warp_sub=torch.stack([w.detach() for w in warps]).numpy().ravel()[::st].copy(),

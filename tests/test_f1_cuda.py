@@ -117,6 +117,19 @@ def test_backward_vs_oracle(name):
         s = np.abs(ref).max() + 1e-12
         tol = 3e-3 if nmis == 0 else 3e-2
         assert np.abs(gT - ref).max() <= tol * s, (k, nmis, np.abs(gT - ref).max(), s)
+    # d loss / d disp against the reference's autograd (full map for the small cases, every 37th / 499th pixel at the
+    # BASELINE sizes cfg1 .. cfg5).  Tolerance: 1e-3 of the gradient scale + 1e-3 relative (north_star: 1e-3), on all but
+    # <= 1e-3 of the pixels (a pixel whose argmin tie broke the other way moves its whole gradient to another source).
+    gdn = gd.cpu().numpy()
+    if "grad_disp" in g:
+        got, want = gdn, g["grad_disp"]
+    else:
+        got, want = gdn.ravel()[::int(g["stride"])], g["grad_disp_sub"]
+    scale = np.abs(want).max()
+    bad = np.abs(got - want) > 1e-3 * scale + 1e-3 * np.abs(want)
+    assert bad.mean() <= 1e-3, (bad.mean(), np.abs(got - want).max(), scale)
+    asum = float(np.abs(gdn.astype(np.float64)).sum())
+    assert abs(asum - float(g["grad_disp_abs_sum"])) <= 2e-3 * float(g["grad_disp_abs_sum"])
 
 
 @pytest.mark.parametrize("shape", [(1, 3, 3), (1, 5, 7), (3, 17, 33), (2, 32, 64), (1, 48, 100), (2, 96, 320)])
