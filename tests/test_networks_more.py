@@ -109,3 +109,28 @@ def test_ifrnet_matches_reference(scale):
     _close(f1[:, :, 1::2, 1::2], g["flow1"], 1e-4), _close(mk[:, :, ::2, ::2], g["mask"], 1e-4)
     with pytest.raises(NotImplementedError):
         m(img0, img1, embt, imgt=img0)
+
+
+@pytest.mark.parametrize("name", ["resnet18_depth", "pose", "dhrnet", "litemono", "fusion_resnet18"])
+def test_train_gradients_match_reference_on_cpu(name):
+    """Module wiring of forward AND backward (train mode) against the reference's autograd, on the host (torch ops):
+    the GPU twin (tests/test_networks_cuda.py) holds the tcgen05 path to the same fixtures."""
+    import netgrad_cases as NC
+    from mono_vifi_b200 import networks
+    g = np.load(os.path.join(GOLD, "netgrad_%s.npz" % name))
+    torch.manual_seed(0)
+    mods, run = NC.build(name, networks)
+    for m in mods:
+        net_fill.fill_(m)
+        m.train()
+    outs = run(mods)
+    NC.loss_of(outs).backward()
+    rec = NC.record(mods, outs)
+    for i in range(len(outs)):
+        scale = max(1e-6, float(np.abs(g["out_%d" % i]).max()))
+        assert float(np.abs(rec["out_%d" % i] - g["out_%d" % i]).max()) <= 1e-4 * scale
+    assert list(rec["names"]) == list(g["names"])
+    assert np.all(np.abs(rec["gsum"] - g["gsum"]) <= 2e-4 * g["gabs"] + 1e-7)
+    assert np.all(np.abs(rec["gabs"] - g["gabs"]) <= 2e-4 * g["gabs"] + 1e-7)
+    for k in ("g_first", "g_last"):
+        assert float(np.abs(rec[k] - g[k]).max()) <= 2e-4 * max(1e-9, float(np.abs(g[k]).max()))
