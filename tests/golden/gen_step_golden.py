@@ -68,4 +68,15 @@ for backbone in ("ResNet18", "DHRNet", "ResNet18_affine"):
     _, losses = tr.process_batch(inp)
     out[key] = {k: float(v) for k, v in losses.items()}
     print(key, out[key])
+    # every parameter gradient of the step (reference autograd): sum and abs-sum per tensor
+    losses["loss"].backward()
+    names, gsum, gabs = [], [], []
+    for mname, mod in m.items():
+        if mname == "encoder_mf":
+            continue
+        for pname, p in mod.named_parameters():
+            names.append("%s.%s" % (mname, pname))
+            gsum.append(0.0 if p.grad is None else float(p.grad.double().sum()))
+            gabs.append(0.0 if p.grad is None else float(p.grad.double().abs().sum()))
+    np.savez_compressed(os.path.join(HERE, "step_grads_%s.npz" % key), names=np.array(names), gsum=np.array(gsum), gabs=np.array(gabs))
 json.dump(out, open(os.path.join(HERE, "step_golden.json"), "w"), indent=1, sort_keys=True)

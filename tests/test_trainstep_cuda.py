@@ -108,8 +108,45 @@ def _golden_inputs(B, H, W, dev):
     return inp
 
 
+# Tolerances of the step-level comparisons with the unmodified reference's CPU fp32 results, per arithmetic class
+# (profiles/r2_net_parity.md explains the classes): (loss_base, loss_dc, per-tensor gradient sums relative to abs-sums).
+# "3xtf32" = this repo's tensor-core kernels at fp32-class accuracy; "cudnn" = the library in fp32 (allow_tf32 = False);
+# "tcgen05" = production TF32 products.  loss_dc is a 1e-3-sized difference of log-depths of two decoders: TF32 input
+# rounding moves it by tens of percent (cuDNN's TF32 does the same), fp32-class arithmetic holds it to 5e-3.
+STEP_TOL = {"cudnn": (1e-3, 5e-3, 5e-2), "tcgen05-3xtf32": (1e-3, 5e-3, 5e-2), "tcgen05": (2e-2, 0.5, None)}
+
+
+def _set_class(backend):
+    from mono_vifi_b200 import conv, conv_tc
+    conv.set_backend("cudnn" if backend == "cudnn" else "tcgen05")
+    conv_tc.precision.set("3xtf32" if backend.endswith("3xtf32") else "tf32")
+
+
+def _check_step_gradients(models, key, tol):
+    """every parameter gradient of the step against the reference's autograd (tests/golden/step_grads_<key>.npz)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_grads_%s.npz" % key))
+    ref = {str(n): (s, a) for n, s, a in zip(g["names"], g["gsum"], g["gabs"])}
+    worst, seen = (0.0, None), 0
+    for mname, mod in models.items():
+        if mname == "encoder_mf":
+            continue
+        for pname, p in mod.named_parameters():
+            s_ref, a_ref = ref["%s.%s" % (mname, pname)]
+            if p.grad is None:
+                assert a_ref == 0.0, (mname, pname)
+                continue
+            seen += 1
+            s, a = float(p.grad.double().sum()), float(p.grad.double().abs().sum())
+            e = max(abs(s - s_ref), abs(a - a_ref)) / max(a_ref, 1e-12)
+            if e > worst[0]:
+                worst = (e, "%s.%s" % (mname, pname))
+    assert seen > 50 and worst[0] <= tol, worst
+    return worst
+
+
 @pytest.mark.parametrize("backbone", ["ResNet18", "DHRNet"])
-@pytest.mark.parametrize("backend", ["cudnn", "tcgen05"])
+@pytest.mark.parametrize("backend", ["cudnn", "tcgen05", "tcgen05-3xtf32"])
 def test_multi_frame_step_matches_reference(backbone, backend):
     """The full multi-frame process_batch (3 VFI passes, 6 pose passes, 6 fused loss groups, 3 SI-log terms) against
     the losses the UNMODIFIED reference computed on CPU for the same inputs and name-keyed weights
@@ -122,7 +159,7 @@ def test_multi_frame_step_matches_reference(backbone, backend):
     gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_golden.json")))
     B, H, W = gold["B"], gold["H"], gold["W"]
     dev = torch.device("cuda:0")
-    conv.set_backend(backend)
+    _set_class(backend)
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
@@ -140,18 +177,20 @@ def test_multi_frame_step_matches_reference(backbone, backend):
         torch.manual_seed(1)
         out = TR.multi_frame_losses(models, vfi, _golden_inputs(B, H, W, dev), opt)
         out["loss"].backward()
-        tol = 2e-3 if backend == "cudnn" else 2e-2   # fp32 vs the TF32 tensor-core path through ~40 layers
+        t_base, t_dc, t_grad = STEP_TOL[backend]
         g = gold[backbone]
-        assert abs(float(out["loss_base"]) - g["loss_base"]) <= tol * g["loss_base"], (float(out["loss_base"]), g["loss_base"])
-        assert abs(float(out["loss_dc"]) - g["loss_dc"]) <= 25 * tol * g["loss_dc"] + 1e-5, (float(out["loss_dc"]), g["loss_dc"])
+        assert abs(float(out["loss_base"]) - g["loss_base"]) <= t_base * g["loss_base"], (float(out["loss_base"]), g["loss_base"])
+        assert abs(float(out["loss_dc"]) - g["loss_dc"]) <= t_dc * g["loss_dc"] + 1e-6, (float(out["loss_dc"]), g["loss_dc"])
         grads = [p.grad for m in models.values() for p in m.parameters() if p.grad is not None]
         assert len(grads) > 50 and all(torch.isfinite(gr).all() for gr in grads)
+        if t_grad is not None and backbone != "DHRNet":   # (D-HRNet at B2 64x96: 12-sample BatchNorm, see r2_net_parity.md)
+            _check_step_gradients(models, backbone, t_grad)
     finally:
         torch.backends.cudnn.allow_tf32 = old
-        conv.set_backend("tcgen05")
+        _set_class("tcgen05")
 
 
-@pytest.mark.parametrize("backend", ["cudnn", "tcgen05"])
+@pytest.mark.parametrize("backend", ["cudnn", "tcgen05", "tcgen05-3xtf32"])
 def test_multi_frame_step_with_affine_branch_matches_reference(backend):
     """process_batch WITH the affine-augmentation branch (train.py:815-883: three more loss groups masked by
     valid_mask_rec with Rc-conjugated poses, three scale-aware depth-consistency terms through the batched
@@ -166,7 +205,7 @@ def test_multi_frame_step_with_affine_branch_matches_reference(backend):
     gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_golden.json")))
     B, H, W = gold["B"], gold["H"], gold["W"]
     dev = torch.device("cuda:0")
-    conv.set_backend(backend)
+    _set_class(backend)
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
@@ -185,15 +224,18 @@ def test_multi_frame_step_with_affine_branch_matches_reference(backend):
         torch.manual_seed(1)
         out = TR.multi_frame_losses(models, vfi, inputs, opt)
         out["loss"].backward()
-        tol = 2e-3 if backend == "cudnn" else 2e-2   # fp32 vs the TF32 tensor-core path through ~40 layers
+        t_base, t_dc, t_grad = STEP_TOL[backend]
         g = gold["ResNet18_affine"]
-        assert abs(float(out["loss_base"]) - g["loss_base"]) <= tol * g["loss_base"], (float(out["loss_base"]), g["loss_base"])
-        assert abs(float(out["loss_dc"]) - g["loss_dc"]) <= 5 * tol * g["loss_dc"] + 1e-5, (float(out["loss_dc"]), g["loss_dc"])
+        assert abs(float(out["loss_base"]) - g["loss_base"]) <= t_base * g["loss_base"], (float(out["loss_base"]), g["loss_base"])
+        # (the affine branch's loss_dc is O(1): scale-aware log-depth differences of rotated / cropped views)
+        assert abs(float(out["loss_dc"]) - g["loss_dc"]) <= min(t_dc, 0.1) * g["loss_dc"] + 1e-6, (float(out["loss_dc"]), g["loss_dc"])
         grads = [p.grad for m in models.values() for p in m.parameters() if p.grad is not None]
         assert len(grads) > 50 and all(torch.isfinite(gr).all() for gr in grads)
+        if t_grad is not None:
+            _check_step_gradients(models, "ResNet18_affine", t_grad)
     finally:
         torch.backends.cudnn.allow_tf32 = old
-        conv.set_backend("tcgen05")
+        _set_class("tcgen05")
 
 
 def test_multi_frame_train_step_litemono_runs():
