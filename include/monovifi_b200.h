@@ -210,15 +210,22 @@ int mvf_act_bwd_bias(const float* grad_y, const float* y, float* grad_pre, float
                      long long P, int C, int act, void* stream);
 
 /* ---- fused torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.step over ONE flat fp32 arena (train.py:661-666) --------
- * params / grads / exp_avg / exp_avg_sq: n floats each, 16-byte aligned.  state[2] (device): {step count, last gradient
- * norm}; the step count is read and incremented on the device, so the call can be recorded into a CUDA graph.
- * max_norm <= 0 disables clipping.  workspace: mvf_adamw_workspace_bytes() bytes of scratch (gradient-norm partials,
- * added in a fixed order).  Same arithmetic as torch's (decoupled weight decay, bias-corrected moments, eps outside the
- * square root). */
+ * params / grads / exp_avg / exp_avg_sq: n floats each, 16-byte aligned.
+ * state[4] (device): {step count, last gradient norm, learning rate, gradient scale}.  The step count is read and
+ * incremented on the device and the learning rate / scale are read there, so the call can be recorded into a CUDA graph
+ * and still follow a scheduler (train.py:239-242) -- the host writes state[2] before a replay.  The gradient scale
+ * (1 / world size after a sum-all-reduce) is applied before the norm.  max_norm <= 0 disables clipping.
+ * n_duplicated: the first n_duplicated floats (multiple of 4) belong to parameters the reference lists twice in its
+ * optimizer (train.py:198-200, shared encoder): their norm counts twice, their gradient is clipped twice and they take two
+ * AdamW updates per call (their own step counter at 2t - 1 and 2t), as torch.optim.AdamW + clip_grad_norm_ do to a
+ * duplicated list entry.  skip_groups (may be NULL): one byte per 4-float group, non-zero = parameter without a gradient
+ * this step, left untouched (torch skips `grad is None`).  workspace: mvf_adamw_workspace_bytes() bytes of scratch
+ * (gradient-norm partials, added in a fixed order).  Same arithmetic as torch's (decoupled weight decay, bias-corrected
+ * moments, eps outside the square root). */
 size_t mvf_adamw_workspace_bytes(void);
-int mvf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,
-                   void* workspace, size_t workspace_bytes, float lr, float beta1, float beta2, float eps, float weight_decay,
-                   float max_norm, void* stream);
+int mvf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, long long n_duplicated,
+                   const unsigned char* skip_groups, float* state, void* workspace, size_t workspace_bytes, float beta1, float beta2,
+                   float eps, float weight_decay, float max_norm, void* stream);
 
 /* Gathers the per-parameter gradient tensors autograd produced into the flat arena mvf_adamw_step reads (and the one
  * data-parallel all-reduce runs on): grads[i] (device pointer, host array; NULL = no gradient this step, slice zeroed)

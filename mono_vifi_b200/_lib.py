@@ -65,7 +65,7 @@ SIGNATURES = {
     "mvf_conv2d_dgrad_s2": (_i, [_CD, _vp, _vp, _vp, _vp]),
     "mvf_conv2d_dgrad_s2_plan": (_i, [_i, _i, _i, ctypes.POINTER(ctypes.c_int), _i]),
     "mvf_adamw_workspace_bytes": (_sz, []),
-    "mvf_adamw_step": (_i, [_vp, _vp, _vp, _vp, ctypes.c_longlong, _vp, _vp, _sz, _f, _f, _f, _f, _f, _f, _vp]),
+    "mvf_adamw_step": (_i, [_vp, _vp, _vp, _vp, ctypes.c_longlong, ctypes.c_longlong, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _vp]),
     "mvf_gather_grads": (_i, [_vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_longlong),
                               ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, _vp]),
     "mvf_selftest_umma": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

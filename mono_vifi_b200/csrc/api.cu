@@ -383,15 +383,17 @@ unsigned long long mvf_stream_capture_id(void* stream) {
 
 /* ---- fused clip_grad_norm_ + AdamW over a flat arena -------------------------------------------------------------- */
 size_t mvf_adamw_workspace_bytes(void) { return mvf::adamw_workspace_bytes(); }
-int mvf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,
-                   void* workspace, size_t workspace_bytes, float lr, float beta1, float beta2, float eps, float weight_decay,
-                   float max_norm, void* stream) {
+int mvf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, long long n_duplicated,
+                   const unsigned char* skip_groups, float* state, void* workspace, size_t workspace_bytes, float beta1, float beta2,
+                   float eps, float weight_decay, float max_norm, void* stream) {
     if (!params || !grads || !exp_avg || !exp_avg_sq || !state || !workspace || n <= 0) return fail(MVF_ERR_INVALID, "mvf_adamw_step: bad argument");
+    if (n_duplicated < 0 || n_duplicated > n || (n_duplicated & 3) != 0)
+        return fail(MVF_ERR_INVALID, "mvf_adamw_step: n_duplicated must be a multiple of 4 in [0, n]");
     if (workspace_bytes < mvf::adamw_workspace_bytes()) return fail(MVF_ERR_WORKSPACE, "mvf_adamw_step: workspace too small");
     if ((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) != 0)
         return fail(MVF_ERR_INVALID, "mvf_adamw_step: arenas must be 16-byte aligned");
-    MVF_RUN("mvf_adamw_step", mvf::adamw_step(params, grads, exp_avg, exp_avg_sq, n, state, workspace, lr, beta1, beta2, eps,
-                                              weight_decay, max_norm, (cudaStream_t)stream));
+    MVF_RUN("mvf_adamw_step", mvf::adamw_step(params, grads, exp_avg, exp_avg_sq, n, n_duplicated, skip_groups, state, workspace,
+                                              beta1, beta2, eps, weight_decay, max_norm, (cudaStream_t)stream));
 }
 
 int mvf_gather_grads(float* arena, const void* const* grads, const long long* offsets, const long long* sizes, int n_tensors,

@@ -5,8 +5,9 @@
 
 namespace mvf {
 size_t adamw_workspace_bytes();
-cudaError_t adamw_step(float* p, const float* g, float* m, float* v, long long n, float* state, void* workspace, float lr,
-                       float beta1, float beta2, float eps, float wd, float max_norm, cudaStream_t st);
+cudaError_t adamw_step(float* p, const float* g, float* m, float* v, long long n, long long n_dup, const unsigned char* skip,
+                       float* state, void* workspace, float beta1, float beta2, float eps, float wd, float max_norm,
+                       cudaStream_t st);
 // copies n_tensors gradient tensors (host arrays of device pointers / arena offsets / element counts) into the arena;
 // a null source zero-fills its slice
 cudaError_t gather_grads(float* G, const void* const* srcs, const long long* offsets, const long long* sizes, int n_tensors,

@@ -17,30 +17,45 @@ from . import _lib
 
 
 class FlatAdamW:
-    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_norm=0.0, distributed=False):
-        seen, self.candidates = set(), []
+    """params: the parameters to train.  duplicated: parameters the reference's optimizer holds TWICE (train.py:198-200
+    appends `models["encoder"]` and `models["encoder_mf"]`, one module under shared_encoder / shared_all): torch then
+    counts their gradient norm twice, clips them twice and steps them twice per iteration; `reference_duplicates=True` in
+    TrainStep reproduces exactly that, the default (each parameter once) is the semantics the reference's authors
+    presumably intended.  The learning rate lives on the device (`set_lr`), so a captured step follows a scheduler."""
+
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_norm=0.0, distributed=False,
+                 duplicated=()):
+        dup_ids = {id(p) for p in duplicated}
+        seen, first, rest = set(), [], []
         for p in params:
             if p.requires_grad and id(p) not in seen:
                 seen.add(id(p))
-                self.candidates.append(p)
+                (first if id(p) in dup_ids else rest).append(p)
+        self.candidates = first + rest          # duplicated parameters lead the arena
+        self._dup_ids = dup_ids
         self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
         self.distributed = distributed
         self.params = None  # fixed after the first backward
+        self._skip = None
+        self._skip_key = None
 
     # -- first step: find the parameters that got a gradient, build the arenas, adopt the gradients just computed
     def _build(self):
         self.params = [p for p in self.candidates if p.grad is not None]
         dev = self.params[0].device
-        offs, total = [], 0
+        offs, total, n_dup = [], 0, 0
         for p in self.params:
             offs.append(total)
             total += (p.numel() + 3) // 4 * 4  # every tensor starts 16-byte aligned
-        self.n = total
+            if id(p) in self._dup_ids:
+                n_dup = total
+        self.n, self.n_dup = total, n_dup
         self.P = torch.zeros(total, device=dev, dtype=torch.float32)
         self.G = torch.zeros(total, device=dev, dtype=torch.float32)
         self.M = torch.zeros(total, device=dev, dtype=torch.float32)
         self.V = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.state = torch.zeros(2, device=dev, dtype=torch.float32)
+        world = dist.get_world_size() if (self.distributed and dist.is_initialized()) else 1
+        self.state = torch.tensor([0.0, 0.0, float(self.lr), 1.0 / world], device=dev, dtype=torch.float32)
         self.ws = torch.empty(_lib.lib().mvf_adamw_workspace_bytes(), device=dev, dtype=torch.uint8)
         self.offs = offs
         self.sizes = [p.numel() for p in self.params]
@@ -52,6 +67,12 @@ class FlatAdamW:
                 n = p.numel()
                 self.P[o:o + n].copy_(p.data.reshape(-1))
                 p.data = self.P[o:o + n].view(p.shape)
+
+    def set_lr(self, lr):
+        """what a scheduler does to param_groups[...]["lr"] (train.py:289, 668); a device write, visible to graph replays"""
+        self.lr = float(lr)
+        if self.params is not None:
+            self.state[2:3].fill_(self.lr)
 
     def zero_grad(self):
         """call before backward: with .grad None autograd adopts the tensors it computes instead of accumulating"""
@@ -70,21 +91,52 @@ class FlatAdamW:
         st = torch.cuda.current_stream(self.P.device).cuda_stream
         _lib.check(_lib.lib().mvf_gather_grads(self.G.data_ptr(), (ctypes.c_void_p * n)(*ptrs), self._c_offs, self._c_sizes, n, st),
                    "mvf_gather_grads")
+        # parameters without a gradient this step are left untouched by the update (torch skips `grad is None`)
+        missing = tuple(i for i, g in enumerate(grads) if g is None)
+        if missing != self._skip_key:
+            self._skip_key = missing
+            if missing:
+                mask = torch.zeros(self.n // 4, dtype=torch.uint8)
+                for i in missing:
+                    mask[self.offs[i] // 4:(self.offs[i] + self.sizes[i] + 3) // 4] = 1
+                self._skip = mask.to(self.P.device)
+            else:
+                self._skip = None
 
     def step(self):
         if self.params is None:
             self._build()
         self._gather()
         if self.distributed and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.G, op=dist.ReduceOp.SUM)
-            self.G.mul_(1.0 / dist.get_world_size())
+            dist.all_reduce(self.G, op=dist.ReduceOp.SUM)   # the 1 / world scale is applied inside the update kernel
         st = torch.cuda.current_stream(self.P.device).cuda_stream
         from . import conv_tc
         conv_tc.weights_epoch += 1  # the parameters change underneath their tensors' version counters
         _lib.check(_lib.lib().mvf_adamw_step(self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(), self.V.data_ptr(), self.n,
-                                             self.state.data_ptr(), self.ws.data_ptr(), self.ws.numel(), self.lr, self.betas[0],
+                                             self.n_dup, None if self._skip is None else self._skip.data_ptr(),
+                                             self.state.data_ptr(), self.ws.data_ptr(), self.ws.numel(), self.betas[0],
                                              self.betas[1], self.eps, self.weight_decay, self.max_norm, st), "mvf_adamw_step")
 
     @property
     def grad_norm(self):
         return self.state[1]
+
+    # -- checkpointing: the reference saves optimizer.state_dict() in ckpt.pth (train.py:1108-1136)
+    def state_dict(self):
+        if self.params is None:
+            return {"step": 0, "lr": self.lr, "built": False}
+        return {"built": True, "step": float(self.state[0]), "lr": self.lr, "sizes": list(self.sizes),
+                "exp_avg": self.M.detach().cpu().clone(), "exp_avg_sq": self.V.detach().cpu().clone()}
+
+    def load_state_dict(self, sd):
+        self.lr = float(sd["lr"])
+        if not sd.get("built", False):
+            return
+        if self.params is None:
+            raise RuntimeError("FlatAdamW.load_state_dict: run one step (or call build_from_grads) before restoring the moments")
+        if list(sd["sizes"]) != list(self.sizes):
+            raise ValueError("FlatAdamW.load_state_dict: parameter layout differs from the checkpoint's")
+        self.M.copy_(sd["exp_avg"])
+        self.V.copy_(sd["exp_avg_sq"])
+        self.state[0:1].fill_(float(sd["step"]))
+        self.state[2:3].fill_(self.lr)

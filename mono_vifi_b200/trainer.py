@@ -31,7 +31,14 @@ class Options:
         self.num_scales = 1
         self.backbone = "ResNet18"              # ResNet18 | ResNet50 | DHRNet | LiteMono   (options.py:187-190)
         self.fuse_model_type = "shared_encoder"  # shared_encoder | separate_all | shared_all (options.py:196-200)
-        self.vfi_scale = "small"                # IFRNet size (options.py:191-195)
+        # IFRNet size of the TRAINING step.  The reference hard-codes IFRNet("large") there (train.py:210) -- its
+        # --vfi_scale (options.py:191-195) only picks the test-time model -- so "large" is the default; BASELINE.json
+        # configs[3] names IFRNet_S for the Lite-Mono configuration and sets "small" explicitly.
+        self.vfi_scale = "large"
+        # True: reproduce the reference's optimizer quirk (train.py:198-200): parameters of a module that sits under two
+        # keys of self.models (encoder / encoder_mf, and depth / depth_mf under shared_all) are held twice by AdamW and
+        # by clip_grad_norm_ -- norm counted twice, clipped twice, stepped twice per iteration.  False: each once.
+        self.reference_duplicates = False
         self.lamda = 0.2                        # weight of the depth-consistency loss (options.py:92-95)
         self.multi_frame = False                # False: the single-frame slice (BASELINE configs[1]); True: full process_batch
         self.tie_break_noise = True  # train.py:1023: torch.randn * 1e-5 on the identity terms
@@ -227,13 +234,19 @@ class TrainStep:
         self.models = models if models is not None else build_models(opt, device)
         # the frozen VFI network of the multi-frame branch (train.py:210-216); not trained, not in the optimizer
         self.vfi = N.IFRNet(opt.vfi_scale).to(device).eval() if opt.multi_frame else None
-        # the reference appends every model's parameters (train.py:198-200; shared modules appear once here)
-        seen, self.params = set(), []
+        # the reference appends every model's parameters (train.py:198-200); a module under two keys is listed twice
+        seen, self.params, self.duplicated = {}, [], []
         for m in self.models.values():
             for p in m.parameters():
                 if id(p) not in seen:
-                    seen.add(id(p))
+                    seen[id(p)] = 1
                     self.params.append(p)
+                else:
+                    seen[id(p)] += 1
+                    if seen[id(p)] == 2:
+                        self.duplicated.append(p)
+        if not getattr(opt, "reference_duplicates", False):
+            self.duplicated = []
         # default on CUDA: clip + AdamW (+ the gradient all-reduce) over flat arenas, two kernel launches per step
         # (optim.FlatAdamW); otherwise torch.optim.AdamW (capturable: step counters on the device for CUDA graphs)
         if fused_optimizer is None:
@@ -244,9 +257,10 @@ class TrainStep:
         if fused_optimizer:
             from .optim import FlatAdamW
             self.flat = FlatAdamW(self.params, lr=opt.learning_rate, weight_decay=opt.weight_decay,
-                                  max_norm=float(opt.clip_grad or 0.0), distributed=distributed)
+                                  max_norm=float(opt.clip_grad or 0.0), distributed=distributed, duplicated=self.duplicated)
         else:
-            self.optimizer = torch.optim.AdamW(self.params, lr=opt.learning_rate, weight_decay=opt.weight_decay,
+            # (torch keeps a duplicated list entry: it warns and steps it twice, which is the reference's behaviour)
+            self.optimizer = torch.optim.AdamW(self.params + self.duplicated, lr=opt.learning_rate, weight_decay=opt.weight_decay,
                                                capturable=bool(capturable and device.type == "cuda"))
             self.reducer = FlatGradAllReduce(self.params) if distributed else None
         # All training work runs on one dedicated (non-default) stream.  autograd binds each parameter's gradient
@@ -268,6 +282,15 @@ class TrainStep:
     def train(self):
         for m in self.models.values():
             m.train()
+
+    def set_lr(self, lr):
+        """the scheduler's write to param_groups[..]["lr"] (train.py:289, 668); takes effect in the next step, also when
+        that step is a CUDA-graph replay (the fused optimiser reads the rate from device memory)"""
+        if self.flat is not None:
+            self.flat.set_lr(lr)
+        else:
+            for g in self.optimizer.param_groups:
+                g["lr"] = lr
 
     def forward_backward(self, inputs):
         if self.flat is not None:
@@ -294,7 +317,7 @@ class TrainStep:
             self.flat.step()  # all-reduce (N > 1) + clip + AdamW
         else:
             if self.opt.clip_grad is not None and self.opt.clip_grad > 0:
-                torch.nn.utils.clip_grad_norm_([p for p in self.params if p.grad is not None], self.opt.clip_grad)
+                torch.nn.utils.clip_grad_norm_([p for p in self.params + self.duplicated if p.grad is not None], self.opt.clip_grad)
             self.optimizer.step()
         loss = out["loss"].detach()
         for m in self.models.values():  # the reference's modules keep their last activations; drop the graph they hold
@@ -348,6 +371,10 @@ class GraphedTrainStep:
         if inputs is not None:
             self.load(inputs)
         self.graph.replay()  # launched on the caller's current stream; the static buffers order it after load()
+        # the replay changed every weight without touching the tensors' version counters: packed filter banks cached by an
+        # eager forward outside the graph (validation, smoke tests) must not be reused afterwards
+        from . import conv_tc
+        conv_tc.weights_epoch += 1
         return self.static_loss
 
 

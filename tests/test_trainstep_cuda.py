@@ -244,7 +244,7 @@ def test_multi_frame_train_step_litemono_runs():
     import torch
     from mono_vifi_b200 import conv, trainer as TR
     dev = torch.device("cuda:0")
-    opt = TR.Options(batch_size=1, height=192, width=640, backbone="LiteMono", multi_frame=True)
+    opt = TR.Options(batch_size=1, height=192, width=640, backbone="LiteMono", multi_frame=True, vfi_scale="small")
     torch.manual_seed(0)
     step = TR.TrainStep(opt, dev)
     step.train()
@@ -287,6 +287,96 @@ def test_flat_adamw_matches_torch():
             assert torch.allclose(pa, pb, rtol=2e-5, atol=2e-6), it
     assert torch.equal(unused.detach(), unused0) and unused.grad is None
     assert float(flat.state[0]) == 5.0
+
+
+def test_flat_adamw_duplicates_schedule_and_missing_gradients():
+    """(a) parameters listed twice (train.py:198-200) against torch's own treatment of a duplicated list entry: norm counted
+    twice, gradient clipped twice, two updates per step (single-tensor implementation, the one the reference's pinned
+    torch 1.11 runs); (b) a learning-rate change between steps; (c) a parameter whose gradient is missing on a later
+    step stays untouched (no weight decay, no moment decay), as torch skips `grad is None`; (d) state_dict round trip."""
+    import torch
+    from mono_vifi_b200.optim import FlatAdamW
+    torch.manual_seed(1)
+    dev = torch.device("cuda:0")
+    mk = lambda: torch.nn.ModuleList([torch.nn.Linear(19, 23), torch.nn.Linear(23, 7), torch.nn.Linear(7, 5)]).to(dev)
+    a, b = mk(), mk()
+    b.load_state_dict(a.state_dict())
+    fwd = lambda m, x, use_last: (m[2](m[1](torch.tanh(m[0](x)))) if use_last else m[1](torch.tanh(m[0](x)))).pow(2).sum()
+    pa, pb = list(a.parameters()), list(b.parameters())
+    dup_a, dup_b = list(a[0].parameters()), list(b[0].parameters())
+    ref = torch.optim.AdamW(pa + dup_a, lr=1e-2, weight_decay=0.05, foreach=False)
+    flat = FlatAdamW(pb, lr=1e-2, weight_decay=0.05, max_norm=0.7, duplicated=dup_b)
+    for it in range(6):
+        x = torch.randn(16, 19, device=dev)
+        use_last = it < 3           # from step 3 on the last layer gets no gradient
+        if it == 2:
+            for g in ref.param_groups:
+                g["lr"] = 3e-3
+            flat.set_lr(3e-3)
+        ref.zero_grad(set_to_none=True)
+        fwd(a, x, use_last).backward()
+        norm = torch.nn.utils.clip_grad_norm_([p for p in pa + dup_a if p.grad is not None], 0.7, foreach=False)
+        ref.step()
+        flat.zero_grad()
+        fwd(b, x, use_last).backward()
+        flat.step()
+        assert abs(float(flat.grad_norm) - float(norm)) <= 1e-4 * float(norm), it
+        for qa, qb in zip(pa, pb):
+            assert torch.allclose(qa, qb, rtol=3e-5, atol=3e-6), it
+    assert flat.n_dup == sum((p.numel() + 3) // 4 * 4 for p in dup_b)
+    sd = flat.state_dict()
+    flat2 = FlatAdamW(pb, lr=1.0, weight_decay=0.05, max_norm=0.7, duplicated=dup_b)
+    flat2.zero_grad()
+    fwd(b, torch.randn(16, 19, device=dev), True).backward()
+    flat2._build()
+    flat2.load_state_dict(sd)
+    assert flat2.lr == 3e-3 and float(flat2.state[0]) == 6.0 and torch.equal(flat2.M, flat.M) and torch.equal(flat2.V, flat.V)
+
+
+def test_graph_replay_invalidates_cached_filter_banks():
+    """An eager forward between graph replays must see the weights the replays produced (the packed-filter cache is keyed
+    on an epoch that every replay bumps), and N graphed steps must equal N eager steps."""
+    import copy
+    import torch
+    from mono_vifi_b200 import conv_tc, trainer as TR
+    dev = torch.device("cuda:0")
+    opt = TR.Options(batch_size=2, height=64, width=96, tie_break_noise=False)
+    torch.manual_seed(11)
+    base = TR.build_models(opt, dev)
+    inputs = TR.synthetic_inputs(opt, dev, seed=6)
+    x = inputs[("color_aug", 0, 0)]
+
+    def eager_disp(models):
+        for m in models.values():
+            m.eval()
+        with torch.no_grad():
+            d = models["depth"](models["encoder"](x))[("disp", 0)].clone()
+        for m in models.values():
+            m.train()
+        return d
+
+    m_g = copy.deepcopy(base)
+    step_g = TR.TrainStep(opt, dev, models=m_g)
+    step_g.train()
+    runner = TR.GraphedTrainStep(step_g, inputs, warmup=2)   # 2 eager + 1 captured (capture does not execute)
+    d0 = eager_disp(m_g)                 # packs and caches the filter banks outside the graph
+    for _ in range(3):
+        runner(inputs)
+    torch.cuda.synchronize()
+    d1 = eager_disp(m_g)                 # must NOT reuse the banks packed for d0
+    fresh = copy.deepcopy(m_g)           # same weights, no cache entries (new Parameter objects)
+    d1_fresh = eager_disp(fresh)
+    assert not torch.equal(d0, d1)
+    assert torch.equal(d1, d1_fresh)
+    # graph vs eager: 2 warm-up + 3 replayed steps against 5 eager steps on a copy
+    m_e = copy.deepcopy(base)
+    step_e = TR.TrainStep(opt, dev, models=m_e)
+    step_e.train()
+    for _ in range(5):
+        step_e(inputs)
+    torch.cuda.synchronize()
+    d_e = eager_disp(m_e)
+    assert float((d_e - d1).abs().max()) <= 2e-3 * float(d_e.abs().max()), float((d_e - d1).abs().max())
 
 
 def test_concurrent_streams_match_the_serial_step():
