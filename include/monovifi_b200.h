@@ -201,6 +201,26 @@ int mvf_bn_relu_bwd(const float* x, const float* grad_y, const float* y, const f
                     const float* save_invstd, float* grad_x, float* grad_identity, float* grad_gamma, float* grad_beta,
                     float* workspace, size_t workspace_floats, long long P, int C, int relu, void* stream);
 
+/* ---- SyncBatchNorm (train.py:205-208: nn.SyncBatchNorm.convert_sync_batchnorm under data parallelism) -----------------
+ * The same kernels split around a cross-rank SUM of `sums`, [2C + 1] doubles {sum_0[C], sum_1[C], pixel count}:
+ *   forward : mvf_bn_sync_stats_fwd (this rank's sum x, sum x^2, count) -> all-reduce(sum) -> mvf_bn_sync_apply_fwd
+ *             (mean / biased variance over the GLOBAL count, running statistics with the global unbiased variance, apply);
+ *   backward: mvf_bn_sync_stats_bwd (this rank's sum g, sum g*xhat; grad_beta / grad_gamma are these LOCAL sums, as in
+ *             torch.nn.SyncBatchNorm -- they are averaged with every other parameter gradient) -> all-reduce(sum) ->
+ *             mvf_bn_sync_apply_bwd (input gradient with the two means taken over the global count).
+ * The exchange itself is the caller's (torch.distributed all_reduce on the float64 vector, NCCL over NVLink).
+ * scratch of mvf_bn_sync_apply_bwd: 2C + 4 floats. */
+int mvf_bn_sync_stats_fwd(const float* x, double* sums, float* workspace, size_t workspace_floats, long long P, int C, void* stream);
+int mvf_bn_sync_apply_fwd(const float* x, const float* identity, float* y, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, long long* num_batches_tracked, float* save_mean, float* save_invstd,
+                          const double* global_sums, long long P, int C, float eps, float momentum, int relu, void* stream);
+int mvf_bn_sync_stats_bwd(const float* x, const float* grad_y, const float* y, const float* save_mean, const float* save_invstd,
+                          double* sums, float* grad_gamma, float* grad_beta, float* workspace, size_t workspace_floats, long long P,
+                          int C, int relu, void* stream);
+int mvf_bn_sync_apply_bwd(const float* x, const float* grad_y, const float* y, const float* gamma, const float* save_mean,
+                          const float* save_invstd, float* grad_x, float* grad_identity, const double* global_sums, float* scratch,
+                          size_t scratch_floats, long long P, int C, int relu, void* stream);
+
 /* Backward of the activation fused into a convolution's epilogue plus the bias gradient, one pass over dense
  * channels-last [P pixels][C]: grad_pre = grad_y * act'(y) (act 0 none, 1 relu, 2 elu(alpha=1), from the saved OUTPUT y)
  * and grad_bias[c] = sum_p grad_pre[p][c] (fixed-order, reproducible).  Replaces elu_backward / threshold_backward +

@@ -60,6 +60,10 @@ SIGNATURES = {
     "mvf_bn_relu_fwd": (_i, [_vp] * 11 + [_sz, ctypes.c_longlong, _i, _f, _f, _i, _vp]),
     "mvf_bn_relu_bwd": (_i, [_vp] * 11 + [_sz, ctypes.c_longlong, _i, _i, _vp]),
     "mvf_act_bwd_bias": (_i, [_vp] * 5 + [_sz, ctypes.c_longlong, _i, _i, _vp]),
+    "mvf_bn_sync_stats_fwd": (_i, [_vp, _vp, _vp, _sz, ctypes.c_longlong, _i, _vp]),
+    "mvf_bn_sync_apply_fwd": (_i, [_vp] * 11 + [ctypes.c_longlong, _i, _f, _f, _i, _vp]),
+    "mvf_bn_sync_stats_bwd": (_i, [_vp] * 9 + [_sz, ctypes.c_longlong, _i, _i, _vp]),
+    "mvf_bn_sync_apply_bwd": (_i, [_vp] * 10 + [_sz, ctypes.c_longlong, _i, _i, _vp]),
     "mvf_stream_capture_id": (ctypes.c_ulonglong, [_vp]),
     "mvf_conv2d_dgrad_s2_supported": (_i, [_CD]),
     "mvf_conv2d_dgrad_s2": (_i, [_CD, _vp, _vp, _vp, _vp]),

@@ -81,6 +81,95 @@ class _BNAct(torch.autograd.Function):
         return gx, gid, dgamma, dbeta, None, None, None, None, None, None
 
 
+# ---- SyncBatchNorm (train.py:205-208) -----------------------------------------------------------------------------------
+# A BatchNorm the reference's `nn.SyncBatchNorm.convert_sync_batchnorm` has converted (or TrainStep(distributed=True) did
+# the same way) normalises with the statistics of ALL ranks.  Same kernels, split around one all-reduce of a
+# [2C + 1] float64 vector per call (sum, sum of squares / sum g, sum g*xhat, pixel count) on the module's process group.
+# Collectives issued from different CUDA streams (the concurrent pose / depth branches) use one NCCL communicator per
+# stream (`group_for_stream`) so that they neither serialise nor interleave differently across ranks.
+_groups = {}
+
+
+def group_for_stream(base_group, stream):
+    import torch.distributed as dist
+    key = (id(base_group), stream.cuda_stream)
+    g = _groups.get(key)
+    if g is None:
+        first = not any(k[0] == id(base_group) for k in _groups)
+        # the first stream that asks keeps the module's own group; further streams get their own communicator.  Every
+        # rank runs the same program, so every rank creates the groups in the same order (new_group is collective).
+        g = base_group if first else dist.new_group(ranks=dist.get_process_group_ranks(base_group) if base_group is not None else None)
+        _groups[key] = g
+    return g
+
+
+def _sync_world(bn):
+    import torch.distributed as dist
+    if not isinstance(bn, torch.nn.SyncBatchNorm) or not dist.is_available() or not dist.is_initialized():
+        return None, 1
+    group = bn.process_group if bn.process_group is not None else dist.group.WORLD
+    return group, dist.get_world_size(group)
+
+
+class _BNActSync(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, identity, weight, bias, running_mean, running_var, nbt, eps, momentum, relu, group):
+        import torch.distributed as dist
+        x = _dense_cl(x)
+        B, C, H, W = x.shape
+        P = B * H * W
+        if identity is not None:
+            identity = _dense_cl(identity)
+        y = torch.empty(B, H, W, C, device=x.device, dtype=torch.float32).permute(0, 3, 1, 2)
+        mean = torch.empty(C, device=x.device, dtype=torch.float32)
+        invstd = torch.empty(C, device=x.device, dtype=torch.float32)
+        sums = torch.empty(2 * C + 1, device=x.device, dtype=torch.float64)
+        L = _lib.lib()
+        ws = _workspace(x.device, L.mvf_bn_workspace_floats(P, C))
+        cur = torch.cuda.current_stream(x.device)
+        st = cur.cuda_stream
+        launches["bn_fwd"] += 1
+        launches["bn_sync"] = launches.get("bn_sync", 0) + 1
+        _lib.check(L.mvf_bn_sync_stats_fwd(x.data_ptr(), sums.data_ptr(), ws.data_ptr(), ws.numel(), P, C, st), "mvf_bn_sync_stats_fwd")
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group_for_stream(group, cur))
+        _lib.check(L.mvf_bn_sync_apply_fwd(x.data_ptr(), None if identity is None else identity.data_ptr(), y.data_ptr(),
+                                           weight.data_ptr(), bias.data_ptr(), None if running_mean is None else running_mean.data_ptr(),
+                                           None if running_var is None else running_var.data_ptr(),
+                                           None if nbt is None else nbt.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                           sums.data_ptr(), P, C, eps, momentum, 1 if relu else 0, st), "mvf_bn_sync_apply_fwd")
+        ctx.save_for_backward(x, y, weight, mean, invstd)
+        ctx.relu, ctx.has_identity, ctx.group = relu, identity is not None, group
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        import torch.distributed as dist
+        x, y, weight, mean, invstd = ctx.saved_tensors
+        B, C, H, W = x.shape
+        P = B * H * W
+        gy = _dense_cl(gy)
+        gx = torch.empty(B, H, W, C, device=x.device, dtype=torch.float32).permute(0, 3, 1, 2)
+        gid = torch.empty(B, H, W, C, device=x.device, dtype=torch.float32).permute(0, 3, 1, 2) if (
+            ctx.has_identity and ctx.needs_input_grad[1]) else None
+        dgamma = torch.empty(C, device=x.device, dtype=torch.float32)
+        dbeta = torch.empty(C, device=x.device, dtype=torch.float32)
+        sums = torch.empty(2 * C + 1, device=x.device, dtype=torch.float64)
+        scratch = torch.empty(2 * C + 4, device=x.device, dtype=torch.float32)
+        L = _lib.lib()
+        ws = _workspace(x.device, L.mvf_bn_workspace_floats(P, C))
+        cur = torch.cuda.current_stream(x.device)
+        st = cur.cuda_stream
+        launches["bn_bwd"] += 1
+        _lib.check(L.mvf_bn_sync_stats_bwd(x.data_ptr(), gy.data_ptr(), y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), sums.data_ptr(),
+                                           dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), ws.numel(), P, C, 1 if ctx.relu else 0, st),
+                   "mvf_bn_sync_stats_bwd")
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group_for_stream(ctx.group, cur))
+        _lib.check(L.mvf_bn_sync_apply_bwd(x.data_ptr(), gy.data_ptr(), y.data_ptr(), weight.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                           gx.data_ptr(), None if gid is None else gid.data_ptr(), sums.data_ptr(), scratch.data_ptr(),
+                                           scratch.numel(), P, C, 1 if ctx.relu else 0, st), "mvf_bn_sync_apply_bwd")
+        return gx, gid, dgamma, dbeta, None, None, None, None, None, None, None
+
+
 def usable(bn, x):
     return (enabled and bn.training and x.is_cuda and x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[1] <= 1024 and
             bn.affine and bn.momentum is not None and x.dtype == torch.float32)
@@ -132,10 +221,16 @@ def bn_act(bn, x, identity=None, relu=True):
             C = rm.numel()
             tmp = torch.zeros(2 * C, device=x.device, dtype=torch.float32)
             _deferred.append((bn, tmp, float(bn.momentum)))
+            group, world = _sync_world(bn)
+            if world > 1:
+                return _BNActSync.apply(x, identity, bn.weight, bn.bias, tmp[:C], tmp[C:], None, float(bn.eps), 1.0, bool(relu), group)
             return _BNAct.apply(x, identity, bn.weight, bn.bias, tmp[:C], tmp[C:], None, float(bn.eps), 1.0, bool(relu))
         if nbt is not None and nbt.dtype != torch.int64:
             nbt.add_(1)
             nbt = None
+        group, world = _sync_world(bn)
+        if world > 1:
+            return _BNActSync.apply(x, identity, bn.weight, bn.bias, rm, rv, nbt, float(bn.eps), float(bn.momentum), bool(relu), group)
         return _BNAct.apply(x, identity, bn.weight, bn.bias, rm, rv, nbt, float(bn.eps), float(bn.momentum), bool(relu))
     y = bn(x)
     if identity is not None:

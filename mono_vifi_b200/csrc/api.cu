@@ -362,6 +362,43 @@ int mvf_bn_relu_bwd(const float* x, const float* grad_y, const float* y, const f
                                                 workspace, P, C, relu, (cudaStream_t)stream));
 }
 
+/* ---- SyncBatchNorm: the same arithmetic split around a cross-rank sum of [2C + 1] doubles --------------------------- */
+int mvf_bn_sync_stats_fwd(const float* x, double* sums, float* workspace, size_t workspace_floats, long long P, int C, void* stream) {
+    if (!x || !sums || !workspace || P <= 0 || C <= 0 || (C % 4) || C > 1024)
+        return fail(MVF_ERR_INVALID, "mvf_bn_sync_stats_fwd: bad argument (C % 4 == 0, C <= 1024)");
+    if (workspace_floats < mvf::bn_workspace_floats(P, C)) return fail(MVF_ERR_WORKSPACE, "mvf_bn_sync_stats_fwd: workspace too small");
+    MVF_RUN("mvf_bn_sync_stats_fwd", mvf::bn_sync_stats_fwd(x, sums, workspace, P, C, (cudaStream_t)stream));
+}
+int mvf_bn_sync_apply_fwd(const float* x, const float* identity, float* y, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, long long* num_batches_tracked, float* save_mean, float* save_invstd,
+                          const double* global_sums, long long P, int C, float eps, float momentum, int relu, void* stream) {
+    if (!x || !y || !gamma || !beta || !save_mean || !save_invstd || !global_sums || P <= 0 || C <= 0 || (C % 4) || C > 1024)
+        return fail(MVF_ERR_INVALID, "mvf_bn_sync_apply_fwd: bad argument (C % 4 == 0, C <= 1024)");
+    MVF_RUN("mvf_bn_sync_apply_fwd", mvf::bn_sync_apply_fwd(x, identity, y, gamma, beta, running_mean, running_var, num_batches_tracked,
+                                                            save_mean, save_invstd, global_sums, P, C, eps, momentum, relu,
+                                                            (cudaStream_t)stream));
+}
+int mvf_bn_sync_stats_bwd(const float* x, const float* grad_y, const float* y, const float* save_mean, const float* save_invstd,
+                          double* sums, float* grad_gamma, float* grad_beta, float* workspace, size_t workspace_floats, long long P,
+                          int C, int relu, void* stream) {
+    if (!x || !grad_y || !save_mean || !save_invstd || !sums || !grad_gamma || !grad_beta || !workspace || P <= 0 || C <= 0 ||
+        (C % 4) || C > 1024 || (relu && !y))
+        return fail(MVF_ERR_INVALID, "mvf_bn_sync_stats_bwd: bad argument (C % 4 == 0, C <= 1024)");
+    if (workspace_floats < mvf::bn_workspace_floats(P, C)) return fail(MVF_ERR_WORKSPACE, "mvf_bn_sync_stats_bwd: workspace too small");
+    MVF_RUN("mvf_bn_sync_stats_bwd", mvf::bn_sync_stats_bwd(x, grad_y, y, save_mean, save_invstd, sums, grad_gamma, grad_beta, workspace,
+                                                            P, C, relu, (cudaStream_t)stream));
+}
+int mvf_bn_sync_apply_bwd(const float* x, const float* grad_y, const float* y, const float* gamma, const float* save_mean,
+                          const float* save_invstd, float* grad_x, float* grad_identity, const double* global_sums, float* scratch,
+                          size_t scratch_floats, long long P, int C, int relu, void* stream) {
+    if (!x || !grad_y || !gamma || !save_mean || !save_invstd || !grad_x || !global_sums || !scratch || P <= 0 || C <= 0 || (C % 4) ||
+        C > 1024 || (relu && !y))
+        return fail(MVF_ERR_INVALID, "mvf_bn_sync_apply_bwd: bad argument (C % 4 == 0, C <= 1024)");
+    if (scratch_floats < (size_t)(2 * C + 4)) return fail(MVF_ERR_WORKSPACE, "mvf_bn_sync_apply_bwd: scratch needs 2C + 4 floats");
+    MVF_RUN("mvf_bn_sync_apply_bwd", mvf::bn_sync_apply_bwd(x, grad_y, y, gamma, save_mean, save_invstd, grad_x, grad_identity, global_sums,
+                                                            scratch, P, C, relu, (cudaStream_t)stream));
+}
+
 int mvf_act_bwd_bias(const float* grad_y, const float* y, float* grad_pre, float* grad_bias, float* workspace, size_t workspace_floats,
                      long long P, int C, int act, void* stream) {
     if (!grad_y || P <= 0 || C <= 0 || (C % 4) || C > 1024 || act < 0 || act > 2 || (act && (!y || !grad_pre)) || (!grad_pre && !grad_bias))

@@ -243,6 +243,96 @@ __global__ void bias_finalize_kernel(const float* __restrict__ partial, int nblo
     if (lane == 0) gbias[c] = (float)s;
 }
 
+// ---- cross-rank (SyncBatchNorm) variants ------------------------------------------------------------------------------
+// Under data parallelism the reference converts every BatchNorm to nn.SyncBatchNorm (train.py:205-208): statistics are
+// taken over the batches of ALL ranks.  The per-CTA partials are first reduced to one [2C + 1] vector of doubles per
+// rank {sum_0[C], sum_1[C], pixel count}; the ranks exchange and add those vectors (NCCL all-reduce, or the peer-memory
+// exchange kernel below) and every rank finishes with the global sums.
+//   forward : sum_0 = sum x, sum_1 = sum x^2      -> mean, biased variance over the global count
+//   backward: sum_0 = sum g, sum_1 = sum g * xhat -> the two means of the input gradient over the global count; the
+//             parameter gradients d_beta / d_gamma stay LOCAL sums (they are averaged with all other gradients later).
+__global__ void bn_sums_kernel(const float* __restrict__ partial, int nblocks, int C, double count, double* __restrict__ sums,
+                               float* __restrict__ local0, float* __restrict__ local1) {
+    pdl_sync();
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c == 0 && lane == 0) sums[2 * C] = count;
+    if (c >= C) return;
+    double s = 0.0, ss = 0.0;
+    for (int b = lane; b < nblocks; b += 32) {
+        s += (double)partial[(size_t)b * 2 * C + c];
+        ss += (double)partial[(size_t)b * 2 * C + C + c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane != 0) return;
+    sums[c] = s;
+    sums[C + c] = ss;
+    if (local0) local0[c] = (float)s;     // backward: d_beta
+    if (local1) local1[c] = (float)ss;    //           d_gamma
+}
+
+__global__ void bn_finalize_sync_fwd_kernel(const double* __restrict__ sums, int C, float eps, float momentum, float* __restrict__ mean,
+                                            float* __restrict__ invstd, float* __restrict__ running_mean,
+                                            float* __restrict__ running_var, long long* __restrict__ num_batches_tracked) {
+    pdl_sync();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (num_batches_tracked && c == 0) *num_batches_tracked += 1;
+    if (c >= C) return;
+    const double N = sums[2 * C];
+    const double m = sums[c] / N;
+    double var = sums[C + c] / N - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        const double unbiased = N > 1.0 ? var * N / (N - 1.0) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    }
+}
+
+// global sums -> what bn_apply_bwd_kernel reads: d_beta, d_gamma over all ranks and 1 / (global pixel count)
+__global__ void bn_unpack_sync_bwd_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma_g, float* __restrict__ dbeta_g,
+                                          float* __restrict__ inv_count) {
+    pdl_sync();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0) *inv_count = (float)(1.0 / sums[2 * C]);
+    if (c >= C) return;
+    dbeta_g[c] = (float)sums[c];
+    dgamma_g[c] = (float)sums[C + c];
+}
+
+__global__ void bn_apply_bwd_sync_kernel(const float4* __restrict__ x, const float4* __restrict__ gy, const float4* __restrict__ y,
+                                         float4* __restrict__ gx, float4* __restrict__ gid, const float* __restrict__ mean,
+                                         const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ dgamma,
+                                         const float* __restrict__ dbeta, long long total4, int C4, const float* __restrict__ inv_count,
+                                         int relu) {
+    pdl_sync();
+    const float inv_P = *inv_count;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        const float4 m = *reinterpret_cast<const float4*>(mean + 4 * c), is = *reinterpret_cast<const float4*>(invstd + 4 * c);
+        const float4 ga = *reinterpret_cast<const float4*>(gamma + 4 * c);
+        const float4 dg = *reinterpret_cast<const float4*>(dgamma + 4 * c), db = *reinterpret_cast<const float4*>(dbeta + 4 * c);
+        const float4 v = __ldg(x + i);
+        float4 g = __ldg(gy + i);
+        if (relu) {
+            const float4 o = __ldg(y + i);
+            g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+        }
+        if (gid) gid[i] = g;
+        float4 r;
+        r.x = ga.x * is.x * (g.x - db.x * inv_P - (v.x - m.x) * is.x * dg.x * inv_P);
+        r.y = ga.y * is.y * (g.y - db.y * inv_P - (v.y - m.y) * is.y * dg.y * inv_P);
+        r.z = ga.z * is.z * (g.z - db.z * inv_P - (v.z - m.z) * is.z * dg.z * inv_P);
+        r.w = ga.w * is.w * (g.w - db.w * inv_P - (v.w - m.w) * is.w * dg.w * inv_P);
+        gx[i] = r;
+    }
+}
+
 int partial_blocks(long long P, int C4) {
     const int rows = NT / C4 > 0 ? NT / C4 : 1;
     static int per_sm = 0, min_px = 0;
@@ -293,6 +383,57 @@ cudaError_t bn_backward(const float* x, const float* gy, const float* y, const f
     launch_pdl(bn_apply_bwd_kernel, dim3((unsigned)(apply_blocks(total4))), dim3(NT), (size_t)(0), st, (const float4*)x, (const float4*)gy, (const float4*)y, (float4*)gx,
                                                            (float4*)gidentity, save_mean, save_invstd, gamma, dgamma, dbeta, total4,
                                                            C4, (float)(1.0 / (double)P), relu);
+    return cudaGetLastError();
+}
+
+cudaError_t bn_sync_stats_fwd(const float* x, double* sums, float* workspace, long long P, int C, cudaStream_t st) {
+    const int C4 = C / 4, nb = partial_blocks(P, C4);
+    const int rows = NT / C4 > 0 ? NT / C4 : 1;
+    launch_pdl(bn_partial_kernel<false>, dim3((unsigned)nb), dim3(NT), (size_t)(2 * rows * C4 * sizeof(float4)), st, (const float4*)x,
+               nullptr, nullptr, nullptr, nullptr, workspace, P, C4, 0);
+    launch_pdl(bn_sums_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), (size_t)0, st, (const float*)workspace, nb, C, (double)P, sums,
+               nullptr, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t bn_sync_apply_fwd(const float* x, const float* identity, float* y, const float* gamma, const float* beta,
+                              float* running_mean, float* running_var, long long* num_batches_tracked, float* save_mean,
+                              float* save_invstd, const double* sums, long long P, int C, float eps, float momentum, int relu,
+                              cudaStream_t st) {
+    const int C4 = C / 4;
+    launch_pdl(bn_finalize_sync_fwd_kernel, dim3((unsigned)((C + 127) / 128)), dim3(128), (size_t)0, st, sums, C, eps, momentum, save_mean,
+               save_invstd, running_mean, running_var, num_batches_tracked);
+    const long long total4 = P * C4;
+    launch_pdl(bn_apply_fwd_kernel, dim3((unsigned)(apply_blocks(total4))), dim3(NT), (size_t)0, st, (const float4*)x,
+               (const float4*)identity, (float4*)y, (const float*)save_mean, (const float*)save_invstd, gamma, beta, total4, C4, relu);
+    return cudaGetLastError();
+}
+
+cudaError_t bn_sync_stats_bwd(const float* x, const float* gy, const float* y, const float* save_mean, const float* save_invstd,
+                              double* sums, float* dgamma, float* dbeta, float* workspace, long long P, int C, int relu,
+                              cudaStream_t st) {
+    const int C4 = C / 4, nb = partial_blocks(P, C4);
+    const int rows = NT / C4 > 0 ? NT / C4 : 1;
+    launch_pdl(bn_partial_kernel<true>, dim3((unsigned)nb), dim3(NT), (size_t)(2 * rows * C4 * sizeof(float4)), st, (const float4*)x,
+               (const float4*)gy, (const float4*)y, save_mean, save_invstd, workspace, P, C4, relu);
+    launch_pdl(bn_sums_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), (size_t)0, st, (const float*)workspace, nb, C, (double)P, sums,
+               dbeta, dgamma);
+    return cudaGetLastError();
+}
+
+// scratch: 2C + 4 floats (global d_gamma, d_beta, 1 / count)
+cudaError_t bn_sync_apply_bwd(const float* x, const float* gy, const float* y, const float* gamma, const float* save_mean,
+                              const float* save_invstd, float* gx, float* gidentity, const double* sums, float* scratch,
+                              long long P, int C, int relu, cudaStream_t st) {
+    const int C4 = C / 4;
+    float* dg = scratch;
+    float* db = scratch + C;
+    float* inv = scratch + 2 * C;
+    launch_pdl(bn_unpack_sync_bwd_kernel, dim3((unsigned)((C + 127) / 128)), dim3(128), (size_t)0, st, sums, C, dg, db, inv);
+    const long long total4 = P * C4;
+    launch_pdl(bn_apply_bwd_sync_kernel, dim3((unsigned)(apply_blocks(total4))), dim3(NT), (size_t)0, st, (const float4*)x,
+               (const float4*)gy, (const float4*)y, (float4*)gx, (float4*)gidentity, save_mean, save_invstd, gamma, (const float*)dg,
+               (const float*)db, total4, C4, (const float*)inv, relu);
     return cudaGetLastError();
 }
 

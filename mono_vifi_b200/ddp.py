@@ -45,6 +45,20 @@ def broadcast_parameters(params, src=0):
         dist.broadcast(p.data, src)
 
 
+def broadcast_module_state(modules, src=0):
+    """Parameters AND buffers (BatchNorm running statistics, num_batches_tracked) of every module from rank `src`: what
+    DistributedDataParallel does at construction (train.py:208).  With SyncBatchNorm the buffers then stay identical on
+    every rank, so a checkpoint does not depend on which rank writes it."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    seen = set()
+    for m in modules:
+        for t in list(m.parameters()) + list(m.buffers()):
+            if id(t) not in seen:
+                seen.add(id(t))
+                dist.broadcast(t.data, src)
+
+
 class FlatGradAllReduce:
     def __init__(self, params):
         seen, self.params = set(), []

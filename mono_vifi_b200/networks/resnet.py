@@ -13,7 +13,7 @@ def _shortcut(downsample, x):
     """identity branch: nothing, or the 1x1 strided conv + bn pair (bn through the fused kernels, no activation)"""
     if downsample is None:
         return x
-    if isinstance(downsample, nn.Sequential) and len(downsample) == 2 and isinstance(downsample[1], nn.BatchNorm2d):
+    if isinstance(downsample, nn.Sequential) and len(downsample) == 2 and isinstance(downsample[1], nn.modules.batchnorm._BatchNorm):
         return bn_act(downsample[1], downsample[0](x), None, relu=False)
     return downsample(x)
 

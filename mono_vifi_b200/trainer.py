@@ -39,6 +39,10 @@ class Options:
         # keys of self.models (encoder / encoder_mf, and depth / depth_mf under shared_all) are held twice by AdamW and
         # by clip_grad_norm_ -- norm counted twice, clipped twice, stepped twice per iteration.  False: each once.
         self.reference_duplicates = False
+        # data-parallel runs: BatchNorm statistics over the batches of all ranks, as the reference's
+        # nn.SyncBatchNorm.convert_sync_batchnorm (train.py:205-208) makes them.  False = per-GPU statistics (a deviation
+        # from the reference, kept for A/B timing of what the exchange costs).
+        self.sync_bn = True
         self.lamda = 0.2                        # weight of the depth-consistency loss (options.py:92-95)
         self.multi_frame = False                # False: the single-frame slice (BASELINE configs[1]); True: full process_batch
         self.tie_break_noise = True  # train.py:1023: torch.randn * 1e-5 on the identity terms
@@ -232,6 +236,12 @@ class TrainStep:
     def __init__(self, opt, device, models=None, distributed=False, capturable=False, fused_optimizer=None):
         self.opt, self.device = opt, device
         self.models = models if models is not None else build_models(opt, device)
+        if distributed and device.type == "cuda" and getattr(opt, "sync_bn", True):
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                # train.py:205-208; converts children in place, so modules registered under two keys stay one module
+                for k in list(self.models):
+                    self.models[k] = torch.nn.SyncBatchNorm.convert_sync_batchnorm(self.models[k])
         # the frozen VFI network of the multi-frame branch (train.py:210-216); not trained, not in the optimizer
         self.vfi = N.IFRNet(opt.vfi_scale).to(device).eval() if opt.multi_frame else None
         # the reference appends every model's parameters (train.py:198-200); a module under two keys is listed twice

@@ -1,0 +1,114 @@
+"""Worker of tests/test_ddp_nccl.py (one process per GPU, launched by torch.distributed.run): the data-parallel step on a
+batch sharded over the ranks must produce what ONE process produces on the whole batch --
+  * every parameter gradient after the all-reduce (mean) == the single-process gradient on the global batch,
+  * every BatchNorm buffer (running_mean / running_var / num_batches_tracked) identical on all ranks and == single process,
+which is what the reference gets from SyncBatchNorm + DistributedDataParallel (train.py:205-208).
+Prints one JSON line from rank 0."""
+import copy
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mono_vifi_b200 import conv_tc, ddp, trainer as TR  # noqa: E402
+
+
+def main():
+    rank, local, world = ddp.init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    multi = len(sys.argv) > 1 and sys.argv[1] == "mf"
+    per_rank = 2
+    B = per_rank * world
+    H, W = 64, 96
+    conv_tc.precision.set("3xtf32")     # fp32-class arithmetic so that the comparison is tight
+    opt_g = TR.Options(batch_size=B, height=H, width=W, tie_break_noise=False, multi_frame=multi, vfi_scale="small")
+    opt_l = TR.Options(batch_size=per_rank, height=H, width=W, tie_break_noise=False, multi_frame=multi, vfi_scale="small")
+    torch.manual_seed(21)
+    base = TR.build_models(opt_g, dev)
+    with torch.no_grad():   # pose outputs are ~1e-3 at initialisation: make the warp a real one
+        base["pose"].convs[("pose", 2)].bias.normal_(0, 2.0)
+    ddp.broadcast_module_state(base.values())
+    inputs_g = TR.synthetic_inputs(opt_g, dev, seed=33)
+    inputs_l = {k: v[rank::world].contiguous() for k, v in inputs_g.items()}   # CustomDistributedSampler's strided split
+    torch.manual_seed(5)
+    vfi_state = None
+    # ---- single process, whole batch (every rank computes it; rank 0 reports) ----
+    m_s = copy.deepcopy(base)
+    step_s = TR.TrainStep(opt_g, dev, models=m_s, distributed=False)
+    if multi:
+        vfi_state = copy.deepcopy(step_s.vfi.state_dict())
+        for t in vfi_state.values():
+            dist.broadcast(t, 0)
+        step_s.vfi.load_state_dict(vfi_state)
+    step_s.train()
+    step_s.side = step_s.side2 = None
+    with torch.cuda.stream(step_s.stream):
+        out_s = step_s.forward_backward(inputs_g)
+    torch.cuda.synchronize()
+    # ---- data parallel: this rank's shard, SyncBatchNorm, gradients averaged over the ranks ----
+    m_d = copy.deepcopy(base)
+    step_d = TR.TrainStep(opt_l, dev, models=m_d, distributed=True)
+    if multi:
+        step_d.vfi.load_state_dict(vfi_state)
+    step_d.train()
+    n_sync = sum(isinstance(mod, torch.nn.SyncBatchNorm) for m in m_d.values() for mod in m.modules())
+    with torch.cuda.stream(step_d.stream):
+        out_d = step_d.forward_backward(inputs_l)
+    torch.cuda.synchronize()
+    worst, worst_name, n = 0.0, None, 0
+    num = den = 0.0
+    for (name_s, mod_s), (name_d, mod_d) in zip(m_s.items(), m_d.items()):
+        for (pn, ps), (_, pd) in zip(mod_s.named_parameters(), mod_d.named_parameters()):
+            if ps.grad is None:
+                assert pd.grad is None, (name_s, pn)
+                continue
+            g = pd.grad.detach().clone()
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            g /= world
+            scale = float(ps.grad.abs().max())
+            if scale > 0:
+                e = float((g - ps.grad).abs().max()) / scale
+                if e > worst:
+                    worst, worst_name = e, "%s.%s" % (name_s, pn)
+            num += float((g - ps.grad).double().pow(2).sum())
+            den += float(ps.grad.double().pow(2).sum())
+            n += 1
+    buf_err, buf_spread = 0.0, 0.0
+    for (name_s, mod_s), (_, mod_d) in zip(m_s.items(), m_d.items()):
+        for (bn, bs), (_, bd) in zip(mod_s.named_buffers(), mod_d.named_buffers()):
+            a, b = bs.double(), bd.double()
+            buf_err = max(buf_err, float((a - b).abs().max()) / max(1e-6, float(a.abs().max())))
+            lo, hi = b.clone(), b.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            buf_spread = max(buf_spread, float((hi - lo).abs().max()))
+    loss_d = out_d["loss"].detach().clone()
+    dist.all_reduce(loss_d, op=dist.ReduceOp.SUM)
+    loss_d /= world
+    # ---- one full optimiser step through the flat arena (all-reduce inside FlatAdamW.step): weights stay identical ----
+    with torch.cuda.stream(step_d.stream):
+        step_d.flat.step()
+    torch.cuda.synchronize()
+    w_spread = 0.0
+    for m in m_d.values():
+        for p in m.parameters():
+            lo, hi = p.detach().clone(), p.detach().clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            w_spread = max(w_spread, float((hi - lo).abs().max()))
+    if rank == 0:
+        print(json.dumps({"world": world, "multi_frame": multi, "sync_bn_modules": n_sync, "params_compared": n,
+                          "grad_worst_rel": worst, "grad_worst_name": worst_name, "grad_rel_l2": (num / max(den, 1e-30)) ** 0.5,
+                          "buffer_rel_err_vs_single": buf_err, "buffer_spread_across_ranks": buf_spread,
+                          "loss_single": float(out_s["loss"]), "loss_dp_mean": float(loss_d),
+                          "weight_spread_after_step": w_spread}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

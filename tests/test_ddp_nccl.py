@@ -1,0 +1,37 @@
+"""GPU, needs >= 2 devices (gpurun --gpus 2): data parallelism over NCCL with SyncBatchNorm against ONE process on the
+global batch -- gradients after the all-reduce, BatchNorm buffers, loss (tests/ddp_nccl_worker.py).  The measured
+numbers of the round are kept in profiles/r2_ddp_nccl_n2.json."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(world, mode, port):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "ddp_nccl_worker.py")] + ([mode] if mode else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    return json.loads(line)
+
+
+@pytest.mark.parametrize("mode", ["", "mf"])
+def test_data_parallel_step_equals_single_process_on_the_global_batch(mode):
+    out = _run(2, mode, 29517 if mode else 29516)
+    assert out["sync_bn_modules"] >= 40
+    # fp32-class arithmetic on both sides; the orders of the batch reductions differ (two shards vs one batch)
+    assert out["grad_rel_l2"] <= 2e-4, out             # measured 2e-5 .. 4e-5
+    assert out["grad_worst_rel"] <= 1e-3, out          # measured 1e-4
+    assert out["buffer_rel_err_vs_single"] <= 1e-4, out
+    assert out["buffer_spread_across_ranks"] == 0.0, out       # identical bits on every rank
+    assert abs(out["loss_single"] - out["loss_dp_mean"]) <= 1e-4 * abs(out["loss_single"]), out
+    assert out["weight_spread_after_step"] == 0.0, out         # replicas stay bit-identical after the optimiser step
