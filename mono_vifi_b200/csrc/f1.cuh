@@ -49,6 +49,9 @@ struct F1Args {
 };
 
 cudaError_t launch_f1_forward(const F1Args& a, cudaStream_t stream);
+// persistent TMA / warp-specialised forward (f1_fwd_tma.cu); launch_f1_forward dispatches to it when the shape qualifies
+bool f1_forward_tma_eligible(const F1Args& a);
+cudaError_t launch_f1_forward_tma(const F1Args& a, cudaStream_t stream);
 cudaError_t launch_f1_backward(const F1Args& a, cudaStream_t stream);
 
 }  // namespace mvf
