@@ -25,6 +25,21 @@ if ROOT not in sys.path:
 METRIC = "training images/sec at 192x640 ResNet18, 1/2/4/8 B200; warp+SSIM HBM GB/s"
 UNIT = "images/s"
 WORKLOAD = "ResNet18 single-frame 192x640 batch 12 per GPU (BASELINE configs[1]): 2 pose nets + depth enc/dec + fused warp/SSIM loss group, fwd+bwd+AdamW"
+MF = ("full multi-frame process_batch (train.py:698-885): 3 frozen IFRNet passes, 6 pose passes, single-frame + fused multi-frame depth of "
+      "3 targets, 6 fused warp/SSIM loss groups, 3 SI-log consistency terms, fwd+bwd+AdamW")
+# BASELINE.json configs[1..4] (+ the full multi-frame step of the headline model); Options overrides of trainer.Options
+CONFIGS = {
+    "2": dict(workload=WORKLOAD, opt=dict(batch_size=12, height=192, width=640)),
+    "mf": dict(workload="ResNet18 192x640 batch 12 per GPU, " + MF + ", IFRNet-large as train.py:210 hard-codes",
+               opt=dict(batch_size=12, height=192, width=640, multi_frame=True)),
+    "3": dict(workload="D-HRNet (HRNet18) 192x640 batch 12 per GPU (BASELINE configs[2]), " + MF + ", IFRNet-large",
+              opt=dict(batch_size=12, height=192, width=640, multi_frame=True, backbone="DHRNet")),
+    "4": dict(workload="Lite-Mono 320x1024 batch 6 per GPU (configs/litemono/LiteMono_KITTI_HR.txt:13) + fusion_module + IFRNet_S "
+                       "(BASELINE configs[3]), " + MF,
+              opt=dict(batch_size=6, height=320, width=1024, multi_frame=True, backbone="LiteMono", vfi_scale="small")),
+    "5": dict(workload="D-HRNet 384x1280 batch 8 per GPU (BASELINE configs[4]), " + MF + ", IFRNet-large",
+              opt=dict(batch_size=8, height=384, width=1280, multi_frame=True, backbone="DHRNet")),
+}
 F1_FWD_BYTES_PER_PX = 40.0 + 8.0   # disp 4 + tgt 12 + 2 x src 12 (+ tie-break noise 8)  SURVEY.md 8(d)
 F1_BWD_BYTES_PER_PX = 44.0         # re-read 40, write grad_disp 4
 
@@ -34,16 +49,27 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=12, help="per-GPU batch (configs[1]: 12)")
-    ap.add_argument("--height", type=int, default=192)
-    ap.add_argument("--width", type=int, default=640)
-    ap.add_argument("--cpu-batch", type=int, default=2, help="bounded CPU sample: images per CPU step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-eager"])
+    ap.add_argument("--config", default="2", choices=["2", "mf", "3", "4", "5"],
+                    help="BASELINE.json configs: 2 = ResNet18 single-frame B12 192x640 (headline), mf = the full multi-frame ResNet18 step, "
+                         "3 = D-HRNet full step B12 192x640, 4 = Lite-Mono 320x1024 + IFRNet_S B6, 5 = D-HRNet 384x1280 B8 multi-frame")
+    ap.add_argument("--no-extra", action="store_true", help="skip the informational extra_configs / torch_eager_gpu legs of the N=1 run")
+    ap.add_argument("--no-sync-bn", action="store_true", help="N>1: per-GPU BatchNorm statistics instead of SyncBatchNorm (A/B)")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--cpu-batch", type=int, default=12, help="CPU arm: images per CPU step (the config's batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-optimizer", action="store_true", help="torch clip_grad_norm_ + AdamW instead of the fused flat-arena kernels")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--conv-backend", default=os.environ.get("MVF_CONV_BACKEND", "tcgen05"), choices=["tcgen05", "cudnn"])
-    return ap.parse_args()
+    args = ap.parse_args()
+    o = CONFIGS[args.config]["opt"]
+    args.batch = args.batch or o["batch_size"]
+    args.height = args.height or o["height"]
+    args.width = args.width or o["width"]
+    args.workload = CONFIGS[args.config]["workload"]
+    return args
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -138,7 +164,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": r["steps"], "warmup": max(1, min(args.warmup, 2)), "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "height": args.height, "width": args.width,
+            "config": {"workload": CONFIGS["2"]["workload"], "height": args.height, "width": args.width,
                        "note": "reference path on host CPU cores: ATen convolutions (all threads) + C oracle of the "
                                "view-synthesis/photometric loss, bounded sample of batch %d per step" % args.cpu_batch},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
@@ -208,7 +234,10 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     conv.set_backend(args.conv_backend)
-    opt = TR.Options(batch_size=args.batch, height=args.height, width=args.width)
+    okw = dict(CONFIGS[args.config]["opt"], batch_size=args.batch, height=args.height, width=args.width)
+    if args.no_sync_bn:
+        okw["sync_bn"] = False
+    opt = TR.Options(**okw)
     torch.manual_seed(1234)
     step = TR.TrainStep(opt, dev, distributed=(world > 1), capturable=not args.no_graph,
                         fused_optimizer=not args.torch_optimizer)
@@ -232,11 +261,12 @@ def run_ours(args):
     for k in conv.stats:
         conv.stats[k] = 0
     n_eager = 2
-    side, step.side = step.side, None  # per-kernel event timing wants the kernels alone on the GPU: no concurrent pose branch
+    # per-kernel event timing wants the kernels alone on the GPU: no concurrent pose branches
+    (side, side2), step.side, step.side2 = (step.side, step.side2), None, None
     for i in range(n_eager):
         step(resident[i % 2])
     torch.cuda.synchronize()
-    step.side = side
+    step.side, step.side2 = side, side2
     kt = {"f1_fwd": [], "f1_bwd": []}
     for tag, a, b in fused.timing:
         kt[tag].append(a.elapsed_time(b))
@@ -348,7 +378,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": args.batch * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (tf32 tensor-core convolutions, as torch's cuDNN default)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": args.batch, "global_batch": args.batch * world,
+            "config": {"workload": args.workload, "config_id": args.config, "per_gpu_batch": args.batch, "global_batch": args.batch * world,
                        "height": args.height, "width": args.width, "parallelism": "dp%d" % world,
                        "launch": graph_note, "streams": ("pose passes on side streams concurrent with the depth branch, weight gradients on companion streams"
                                    if step.side is not None else "one stream"),
@@ -361,10 +391,90 @@ def run_ours(args):
             "gpu_launches": my_launches, "clocks": clocks, "loss": last,
             "roofline": roof("f1_fwd", F1_FWD_BYTES_PER_PX), "roofline_bwd": roof("f1_bwd", F1_BWD_BYTES_PER_PX),
             "roofline_conv": conv_roof}
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.config == "2":
         r = time_cpu(args.cpu_batch, args.height, args.width, 3, 1, budget_s=25.0)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    if world == 1 and not args.no_extra and args.config == "2":
+        # informational legs (never the headline): the same step on stock eager PyTorch / cuDNN on this GPU, and the other
+        # BASELINE configs, each in its own process so that a failure there cannot touch the line above
+        del run, feeder, step
+        torch.cuda.empty_cache()
+        try:
+            line["torch_eager_gpu"] = time_torch_eager(args.batch, args.height, args.width, dev, resident, 10, 3)
+        except Exception as e:
+            line["torch_eager_gpu"] = {"error": str(e).splitlines()[0][:200]}
+        line["extra_configs"] = {c: run_extra_config(c) for c in ("mf", "3", "4", "5")}
     emit(line)
+    return 0
+
+
+def time_torch_eager(B, H, W, dev, batches, steps, warmup):
+    """The single-frame step of configs[1] on stock torch (baseline/torch_eager.py): cuDNN convolutions with torch's default
+    TF32 setting, nn.BatchNorm2d, F.grid_sample, unfused loss, torch AdamW, eager launches."""
+    import torch
+    from baseline import torch_eager as TE
+    torch.manual_seed(1234)
+    out = {}
+    for tag, cl in (("nchw", False), ("channels_last", True)):
+        st = TE.SingleFrameStep(B, H, W, dev, channels_last=cl)
+        for i in range(warmup):
+            st(batches[i % 2])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            loss = st(batches[i % 2])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[tag] = {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup, "loss": float(loss)}
+        del st
+        torch.cuda.empty_cache()
+    best = max(out.values(), key=lambda r: r["value"])
+    return {"value": best["value"], "unit": UNIT, "ms_per_step": best["ms_per_step"], "layouts": out,
+            "what": "stock torch %s / cuDNN eager, same step, same batch, inputs resident (baseline/torch_eager.py)" % torch.__version__}
+
+
+def run_extra_config(cfg, steps=5, warmup=3, timeout=170):
+    cmd = [sys.executable, os.path.abspath(__file__), "--config", cfg, "--no-extra", "--no-cpu-baseline", "--steps", str(steps),
+           "--warmup", str(warmup)]
+    t0 = time.perf_counter()
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        rows = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+        if p.returncode != 0 or not rows:
+            return {"error": "exit %d: %s" % (p.returncode, (p.stderr.strip().splitlines() or ["no output"])[-1][:300])}
+        r = json.loads(rows[-1])
+        keep = {k: r.get(k) for k in ("value", "unit", "ms_per_step", "steps", "warmup", "gpu_launches", "loss")}
+        keep["e2e"] = (r.get("e2e") or {}).get("value")
+        keep["workload"] = r["config"]["workload"]
+        for k in ("launch", "conv_calls_per_step", "conv_kernel_launches_per_step", "bn_calls_per_step", "per_gpu_batch", "height", "width"):
+            keep[k] = r["config"].get(k)
+        keep["f1_fwd"] = {k: (r.get("roofline") or {}).get(k) for k in ("avg_launch_us", "frac", "launches_timed")}
+        keep["f1_bwd"] = {k: (r.get("roofline_bwd") or {}).get(k) for k in ("avg_launch_us", "frac", "launches_timed")}
+        keep["conv_frac"] = {k: v.get("frac") for k, v in (r.get("roofline_conv") or {}).items()}
+        keep["wall_s"] = time.perf_counter() - t0
+        return keep
+    except subprocess.TimeoutExpired:
+        return {"error": "timeout after %d s" % timeout}
+    except Exception as e:
+        return {"error": str(e)[:300]}
+
+
+def run_torch_eager(args):
+    """`--impl torch-eager`: the GPU eager-PyTorch arm alone (N=1), printed in the same line format."""
+    import torch
+    from mono_vifi_b200 import trainer as TR
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    dev = torch.device("cuda", 0)
+    opt = TR.Options(batch_size=args.batch, height=args.height, width=args.width)
+    batches = [TR.synthetic_inputs(opt, dev, seed=1234 + s) for s in range(2)]
+    r = time_torch_eager(args.batch, args.height, args.width, dev, batches, args.steps, args.warmup)
+    emit({"impl": "torch-eager", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "f32 (cuDNN TF32 convolutions, torch default)", "data": "synthetic",
+          "config": {"workload": CONFIGS["2"]["workload"], "what": r["what"], "layouts": r["layouts"]}, "gpu_launches": 0})
     return 0
 
 
@@ -396,6 +506,8 @@ def main():
     _reserve_stdout()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "torch-eager":
+        return run_torch_eager(args)
     rc = run_ours(args)
     try:
         import torch.distributed as dist

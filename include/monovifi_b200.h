@@ -170,6 +170,17 @@ size_t mvf_conv2d_wgrad_workspace_floats(const mvf_conv2d_desc* d);
 int mvf_conv2d_wgrad(const mvf_conv2d_desc* d, const float* x, const float* grad_out, float* grad_w, float* workspace,
                      size_t workspace_floats, void* stream);
 
+/* Convolution + bias + nn.PReLU(Cout) in the epilogue: the `convrelu` block of the frozen VFI network (networks/IFRNet.py:121-125,
+ * every encoder / decoder convolution of IFRNet.py:153-330).  Same descriptor / packed bank as mvf_conv2d_forward; slope[Cout]. */
+int mvf_conv2d_forward_prelu(const mvf_conv2d_desc* d, const float* x, const float* w_packed, const float* bias, const float* slope,
+                             float* y, void* stream);
+/* nn.ConvTranspose2d(Cin_t, Cout_t, k, stride 2, padding p) forward (IFRNet.py:194: 4x4, stride 2, padding 1) = the data gradient of
+ * the stride-2 convolution with the same weight tensor, plus bias: four output-parity classes, each a small stride-1 convolution,
+ * one persistent tcgen05 launch (the kernel of mvf_conv2d_dgrad_s2).  d describes that convolution: d->Cout = Cin_t (channels of x),
+ * d->Cin = Cout_t (channels of y), H / W = the OUTPUT size, x_stride = strides of y, y_stride = strides of x; w_packed =
+ * mvf_conv2d_pack_filters(weight viewed as [Cin_t, Cout_t, k, k], dgrad = 1). */
+int mvf_conv_transpose2d_s2_fwd(const mvf_conv2d_desc* d, const float* x, const float* w_packed, const float* bias, float* y, void* stream);
+
 /* ---- fused nearest-upsample x2 + channel concat + ReflectionPad2d(1), channels-last ---------------------------------
  * y[B,Ca+Cs,H+2,W+2] = pad(cat(upsample ? up2(a[B,Ca,H/2,W/2]) : a[B,Ca,H,W], skip[B,Cs,H,W])): the data movement
  * the reference does with F.interpolate + torch.cat + nn.ReflectionPad2d(1) before each decoder convolution
@@ -184,6 +195,34 @@ int mvf_upcat_pad_bwd(const float* grad_y, float* grad_a, float* grad_skip, int 
  * feeds the gather-form (atomic-free, deterministic) backward.  C % 4 == 0; Ho = (H-1)/2+1. */
 int mvf_maxpool3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int C, int H, int W, void* stream);
 int mvf_maxpool3s2_bwd(const float* grad_y, const unsigned char* idx, float* grad_x, int B, int C, int H, int W, void* stream);
+
+/* ---- feature warp ("F2"), bilinear resize, PReLU tail, pose matrices (csrc/warp_cl.cu) -------------------------------------
+ * layout: 0 = dense NCHW (any C), 1 = dense channels-last with C % 2 == 0 (element (b,c,y,x) at ((b*H + y)*W + x)*C + c;
+ * float4 accesses when C % 4 == 0, float2 otherwise).
+ *
+ * mvf_flow_warp_*: IFRNet.warp (networks/IFRNet.py:7-15, used by IFRNet.forward :400-441 and FusionModule.warp_features,
+ *   fusion_module.py:78-90): y[b,:,v,u] = bilinear sample of x[b] at (u + flow[b,0,v,u], v + flow[b,1,v,u]), border padding,
+ *   align_corners=True; flow is NCHW [B,2,H,W] in pixels.  bwd (channels-last only) gives grad_x; it replaces ATen's float-atomic
+ *   grid_sampler_2d_backward by a 64-bit fixed-point scatter (order-independent, bitwise deterministic); workspace:
+ *   mvf_flow_warp_bwd_workspace_bytes(B, C, H, W) bytes of scratch (zeroed by the call).
+ * mvf_resize_bilinear_*: F.interpolate(mode="bilinear", align_corners=...) (hrnet_encoder.py:275-280, IFRNet.py:118,383-423,
+ *   fusion_module.py:68-99, layers.py:225-228 as used by LiteMono.py:495,502); scale_h / scale_w are torch's source-index scales
+ *   (in/out, 1/scale_factor, or (in-1)/(out-1) when align_corners); channel c of an NCHW tensor is multiplied by mul_even / mul_odd
+ *   by parity (the flow rescaling of fusion_module.py:86-87, IFRNet.py:417-421); bwd is the exact adjoint in gather form.
+ * mvf_prelu_cl_fwd: y = PReLU_C(x + res) (res may be NULL), channels-last [P pixels][C]  (IFRNet.py:121-150).
+ * mvf_pose_matrix_*: transformation_from_parameters (layers.py:28-103): axisangle[B,3], translation[B,3] -> M[B,4,4]. */
+int mvf_flow_warp_fwd(const float* x, const float* flow, float* y, int B, int C, int H, int W, int layout, void* stream);
+size_t mvf_flow_warp_bwd_workspace_bytes(int B, int C, int H, int W);
+int mvf_flow_warp_bwd(const float* grad_y, const float* flow, float* grad_x, int B, int C, int H, int W, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int mvf_resize_bilinear_fwd(const float* x, float* y, int B, int C, int Hin, int Win, int Hout, int Wout, float scale_h, float scale_w,
+                            int align_corners, float mul_even, float mul_odd, int layout, void* stream);
+int mvf_resize_bilinear_bwd(const float* grad_y, float* grad_x, int B, int C, int Hin, int Win, int Hout, int Wout, float scale_h,
+                            float scale_w, int align_corners, float mul_even, float mul_odd, int layout, void* stream);
+int mvf_prelu_cl_fwd(const float* x, const float* res, const float* slope, float* y, long long P, int C, void* stream);
+int mvf_pose_matrix_fwd(const float* axisangle, const float* translation, float* M, int B, int invert, void* stream);
+int mvf_pose_matrix_bwd(const float* axisangle, const float* translation, const float* grad_M, float* grad_axisangle,
+                        float* grad_translation, int B, int invert, void* stream);
 
 /* ---- fused training-mode BatchNorm2d (+ residual add) + ReLU on dense channels-last tensors [P pixels][C] -----------
  * The bn -> (+= identity) -> relu tail of torchvision's BasicBlock / Bottleneck (networks/monodepth2.py:16-31,

@@ -49,6 +49,8 @@ SIGNATURES = {
     "mvf_conv2d_pack_filters": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mvf_conv2d_supported": (_i, [_CD]),
     "mvf_conv2d_forward": (_i, [_CD, _vp, _vp, _vp, _vp, _i, _vp]),
+    "mvf_conv2d_forward_prelu": (_i, [_CD, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvf_conv_transpose2d_s2_fwd": (_i, [_CD, _vp, _vp, _vp, _vp, _vp]),
     "mvf_conv2d_wgrad_supported": (_i, [_CD]),
     "mvf_conv2d_wgrad_workspace_floats": (_sz, [_CD]),
     "mvf_conv2d_wgrad": (_i, [_CD, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -64,6 +66,14 @@ SIGNATURES = {
     "mvf_bn_sync_apply_fwd": (_i, [_vp] * 11 + [ctypes.c_longlong, _i, _f, _f, _i, _vp]),
     "mvf_bn_sync_stats_bwd": (_i, [_vp] * 9 + [_sz, ctypes.c_longlong, _i, _i, _vp]),
     "mvf_bn_sync_apply_bwd": (_i, [_vp] * 10 + [_sz, ctypes.c_longlong, _i, _i, _vp]),
+    "mvf_flow_warp_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "mvf_flow_warp_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "mvf_flow_warp_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "mvf_resize_bilinear_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _f, _i, _vp]),
+    "mvf_resize_bilinear_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _f, _i, _vp]),
+    "mvf_prelu_cl_fwd": (_i, [_vp, _vp, _vp, _vp, ctypes.c_longlong, _i, _vp]),
+    "mvf_pose_matrix_fwd": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "mvf_pose_matrix_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "mvf_stream_capture_id": (ctypes.c_ulonglong, [_vp]),
     "mvf_conv2d_dgrad_s2_supported": (_i, [_CD]),
     "mvf_conv2d_dgrad_s2": (_i, [_CD, _vp, _vp, _vp, _vp]),

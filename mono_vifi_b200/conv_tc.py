@@ -11,6 +11,7 @@ import os
 import weakref
 
 import torch
+import torch.nn.functional as F
 
 from . import _lib
 
@@ -134,6 +135,54 @@ def conv_forward_raw(x, w_packed, bias, Cout, KH, KW, pad, stride=1, act=0, out=
 
 
 ACT = {None: 0, "none": 0, "relu": 1, "elu": 2}
+
+
+def conv2d_prelu_inference(x, weight, bias, slope, stride=1, padding=0):
+    """conv + bias + nn.PReLU(Cout) in the kernel's epilogue (mvf_conv2d_forward_prelu): the `convrelu` block of the frozen VFI
+    network (IFRNet.py:121-125).  Forward only."""
+    pad = padding if isinstance(padding, int) else padding[0]
+    x = _as_input(x)
+    B, Cin, H, W = x.shape
+    Cout, _, KH, KW = weight.shape
+    Ho, Wo = out_hw(H, W, KH, KW, pad, stride)
+    y = torch.empty(B, Ho, Wo, Cout, device=x.device, dtype=torch.float32).permute(0, 3, 1, 2)
+    d = _desc(B, Cin, H, W, Cout, KH, KW, pad, stride, x, y)
+    b = None if bias is None else bias.detach().float().contiguous()
+    sl = slope.detach().float().contiguous()
+    launches["fprop"] += 1
+    flops = 2.0 * B * Ho * Wo * Cout * Cin * KH * KW
+    rc = _timed("fprop", flops, lambda: _lib.lib().mvf_conv2d_forward_prelu(
+        d, x.data_ptr(), pack_filters(weight).data_ptr(), None if b is None else b.data_ptr(), sl.data_ptr(), y.data_ptr(), _stream(x)))
+    _lib.check(rc, "mvf_conv2d_forward_prelu")
+    return y
+
+
+def conv_transpose2d_s2_inference(x, weight, bias, padding):
+    """nn.ConvTranspose2d(Cin_t, Cout_t, k, stride 2, padding) forward on the stride-2 data-gradient kernel
+    (mvf_conv_transpose2d_s2_fwd; IFRNet.py:194).  weight [Cin_t, Cout_t, k, k].  Channel counts that are not multiples of 4
+    are zero-padded (weight, bias, and the input's channels) and the result sliced back.  Forward only."""
+    Cin_t, Cout_t, KH, KW = weight.shape
+    B, _, H, W = x.shape
+    Ho, Wo = (H - 1) * 2 - 2 * padding + KH, (W - 1) * 2 - 2 * padding + KW
+    w = weight.detach()
+    b = None if bias is None else bias.detach().float()
+    ep_out, ep_in = (-Cout_t) % 4, (-Cin_t) % 4
+    if ep_out or ep_in:
+        w = F.pad(w, (0, 0, 0, 0, 0, ep_out, 0, ep_in))
+        b = None if b is None else F.pad(b, (0, ep_out))
+        if ep_in:
+            x = F.pad(x, (0, 0, 0, 0, 0, ep_in))
+    x = _as_input(x)
+    Ci, Co = Cin_t + ep_in, Cout_t + ep_out
+    y = torch.empty(B, Ho, Wo, Co, device=x.device, dtype=torch.float32).permute(0, 3, 1, 2)
+    d = _desc(B, Co, Ho, Wo, Ci, KH, KW, padding, 2, y, x)   # the stride-2 convolution whose data gradient this is
+    launches["dgrad"] += 1
+    flops = 2.0 * B * H * W * Ci * Co * KH * KW
+    wp = pack_filters(w if (ep_out or ep_in) else weight, dgrad=True)
+    rc = _timed("dgrad", flops, lambda: _lib.lib().mvf_conv_transpose2d_s2_fwd(
+        d, x.data_ptr(), wp.data_ptr(), None if b is None else b.contiguous().data_ptr(), y.data_ptr(), _stream(x)))
+    _lib.check(rc, "mvf_conv_transpose2d_s2_fwd")
+    return y[:, :Cout_t] if ep_out else y
 
 
 def _dense_cl(t):

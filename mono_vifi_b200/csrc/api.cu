@@ -10,6 +10,7 @@
 #include "ops.cuh"
 #include "ops_cl.cuh"
 #include "optim.cuh"
+#include "warp_cl.cuh"
 
 namespace {
 thread_local char g_err[512] = "";
@@ -262,6 +263,24 @@ int mvf_conv2d_forward(const mvf_conv2d_desc* d, const float* x, const float* w_
     if (e != cudaSuccess) return why ? fail(MVF_ERR_CUDA, why) : fail(MVF_ERR_CUDA, "mvf_conv2d_forward launch", e);
     return MVF_OK;
 }
+int mvf_conv2d_forward_prelu(const mvf_conv2d_desc* d, const float* x, const float* w_packed, const float* bias, const float* slope,
+                             float* y, void* stream) {
+    if (!d || !x || !w_packed || !y || !slope) return fail(MVF_ERR_INVALID, "mvf_conv2d_forward_prelu: null pointer");
+    const mvf::tc::ConvDesc c = to_desc(d);
+    const char* why = mvf::tc::conv_check(c);
+    if (why) return fail(MVF_ERR_INVALID, why);
+    cudaError_t e = mvf::tc::conv_forward(c, x, w_packed, bias, y, 3, (cudaStream_t)stream, &why, slope);
+    if (e != cudaSuccess) return why ? fail(MVF_ERR_CUDA, why) : fail(MVF_ERR_CUDA, "mvf_conv2d_forward_prelu launch", e);
+    return MVF_OK;
+}
+int mvf_conv_transpose2d_s2_fwd(const mvf_conv2d_desc* d, const float* x, const float* w_packed, const float* bias, float* y, void* stream) {
+    if (!d || !x || !w_packed || !y) return fail(MVF_ERR_INVALID, "mvf_conv_transpose2d_s2_fwd: null pointer");
+    const char* why = nullptr;
+    cudaError_t e = mvf::tc::conv_dgrad_s2(to_desc(d), x, w_packed, y, (cudaStream_t)stream, &why, bias);
+    if (e != cudaSuccess)
+        return why ? fail(e == cudaErrorInvalidValue ? MVF_ERR_INVALID : MVF_ERR_CUDA, why) : fail(MVF_ERR_CUDA, "mvf_conv_transpose2d_s2_fwd launch", e);
+    return MVF_OK;
+}
 int mvf_conv2d_dgrad_s2_supported(const mvf_conv2d_desc* d) {
     if (!d) return 0;
     const char* why = mvf::tc::conv_dgrad_s2_check(to_desc(d));
@@ -440,6 +459,56 @@ int mvf_gather_grads(float* arena, const void* const* grads, const long long* of
     for (int i = 0; i < n_tensors; ++i)
         if (offsets[i] < 0 || (offsets[i] & 3) != 0 || sizes[i] < 0) return fail(MVF_ERR_INVALID, "mvf_gather_grads: offsets must be non-negative multiples of 4");
     MVF_RUN("mvf_gather_grads", mvf::gather_grads(arena, grads, offsets, sizes, n_tensors, (cudaStream_t)stream));
+}
+
+int mvf_flow_warp_fwd(const float* x, const float* flow, float* y, int B, int C, int H, int W, int layout, void* stream) {
+    if (!x || !flow || !y || B <= 0 || C <= 0 || H < 2 || W < 2 || (layout != 0 && layout != 1) || (layout == 1 && (C % 2)))
+        return fail(MVF_ERR_INVALID, "mvf_flow_warp_fwd: bad argument (H, W >= 2; channels-last needs C % 2 == 0)");
+    MVF_RUN("mvf_flow_warp_fwd", mvf::flow_warp_fwd(x, flow, y, B, C, H, W, layout, (cudaStream_t)stream));
+}
+size_t mvf_flow_warp_bwd_workspace_bytes(int B, int C, int H, int W) {
+    return (B > 0 && C > 0 && H > 0 && W > 0) ? mvf::flow_warp_bwd_workspace_bytes(B, C, H, W) : 0;
+}
+int mvf_flow_warp_bwd(const float* grad_y, const float* flow, float* grad_x, int B, int C, int H, int W, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+    if (!grad_y || !flow || !grad_x || !workspace || B <= 0 || C <= 0 || (C % 2) || H < 2 || W < 2)
+        return fail(MVF_ERR_INVALID, "mvf_flow_warp_bwd: bad argument (channels-last, C % 2 == 0, H, W >= 2)");
+    if (workspace_bytes < mvf::flow_warp_bwd_workspace_bytes(B, C, H, W) || ((uintptr_t)workspace & 15))
+        return fail(MVF_ERR_INVALID, "mvf_flow_warp_bwd: workspace too small or not 16-byte aligned");
+    MVF_RUN("mvf_flow_warp_bwd", mvf::flow_warp_bwd(grad_y, flow, grad_x, B, C, H, W, workspace, workspace_bytes, (cudaStream_t)stream));
+}
+static bool resize_args_ok(const void* a, const void* b, int B, int C, int Hi, int Wi, int Ho, int Wo, int layout) {
+    return a && b && B > 0 && C > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && (layout == 0 || (layout == 1 && C % 2 == 0));
+}
+int mvf_resize_bilinear_fwd(const float* x, float* y, int B, int C, int Hin, int Win, int Hout, int Wout, float scale_h, float scale_w,
+                            int align_corners, float mul_even, float mul_odd, int layout, void* stream) {
+    if (!resize_args_ok(x, y, B, C, Hin, Win, Hout, Wout, layout)) return fail(MVF_ERR_INVALID, "mvf_resize_bilinear_fwd: bad argument");
+    if (layout == 1 && (mul_even != 1.f || mul_odd != 1.f)) return fail(MVF_ERR_INVALID, "mvf_resize_bilinear_fwd: multipliers are NCHW-only");
+    MVF_RUN("mvf_resize_bilinear_fwd", mvf::resize_bilinear_fwd(x, y, B, C, Hin, Win, Hout, Wout, scale_h, scale_w, align_corners, mul_even,
+                                                                mul_odd, layout, (cudaStream_t)stream));
+}
+int mvf_resize_bilinear_bwd(const float* grad_y, float* grad_x, int B, int C, int Hin, int Win, int Hout, int Wout, float scale_h,
+                            float scale_w, int align_corners, float mul_even, float mul_odd, int layout, void* stream) {
+    if (!resize_args_ok(grad_y, grad_x, B, C, Hin, Win, Hout, Wout, layout)) return fail(MVF_ERR_INVALID, "mvf_resize_bilinear_bwd: bad argument");
+    if (layout == 1 && (mul_even != 1.f || mul_odd != 1.f)) return fail(MVF_ERR_INVALID, "mvf_resize_bilinear_bwd: multipliers are NCHW-only");
+    MVF_RUN("mvf_resize_bilinear_bwd", mvf::resize_bilinear_bwd(grad_y, grad_x, B, C, Hin, Win, Hout, Wout, scale_h, scale_w, align_corners,
+                                                                mul_even, mul_odd, layout, (cudaStream_t)stream));
+}
+int mvf_prelu_cl_fwd(const float* x, const float* res, const float* slope, float* y, long long P, int C, void* stream) {
+    if (!x || !slope || !y || P <= 0 || C <= 0 || (C % 4) || ((uintptr_t)slope & 15))
+        return fail(MVF_ERR_INVALID, "mvf_prelu_cl_fwd: bad argument (C % 4 == 0, 16-byte aligned slope)");
+    MVF_RUN("mvf_prelu_cl_fwd", mvf::prelu_cl_fwd(x, res, slope, y, P, C, (cudaStream_t)stream));
+}
+int mvf_pose_matrix_fwd(const float* axisangle, const float* translation, float* M, int B, int invert, void* stream) {
+    if (!axisangle || !translation || !M || B <= 0) return fail(MVF_ERR_INVALID, "mvf_pose_matrix_fwd: bad argument");
+    MVF_RUN("mvf_pose_matrix_fwd", mvf::pose_matrix_fwd(axisangle, translation, M, B, invert, (cudaStream_t)stream));
+}
+int mvf_pose_matrix_bwd(const float* axisangle, const float* translation, const float* grad_M, float* grad_axisangle,
+                        float* grad_translation, int B, int invert, void* stream) {
+    if (!axisangle || !translation || !grad_M || !grad_axisangle || !grad_translation || B <= 0)
+        return fail(MVF_ERR_INVALID, "mvf_pose_matrix_bwd: bad argument");
+    MVF_RUN("mvf_pose_matrix_bwd", mvf::pose_matrix_bwd(axisangle, translation, grad_M, grad_axisangle, grad_translation, B, invert,
+                                                        (cudaStream_t)stream));
 }
 
 }  // extern "C"

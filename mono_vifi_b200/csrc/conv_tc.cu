@@ -51,7 +51,8 @@ struct ConvArgs {
     int tw_log2;                 // tile = (1 << tw_log2) x (128 >> tw_log2) output pixels
     int tiles_x, tiles_y;
     int n_cblk;                  // ceil(Cin / 32)
-    int act;                     // 0 none, 1 relu, 2 elu
+    int act;                     // 0 none, 1 relu, 2 elu, 3 prelu (per-channel `slope`)
+    const float* slope;
     float* dbg;                  // debug: raw copy of pipeline stage 0 (A then B) of CTA (0,0); null in production
 };
 
@@ -68,7 +69,8 @@ __device__ __forceinline__ float elu_neg(float t) {
 // Branches are on kernel-uniform values only and sit OUTSIDE the element loops (the per-element form cost ~30
 // instructions per value: it was 40 % of the stall samples of the 16-channel decoder layers).
 template <int CH>
-__device__ __forceinline__ void bias_act(float (&v)[CH], const float* __restrict__ bias, int n_first, int Cout, int act) {
+__device__ __forceinline__ void bias_act(float (&v)[CH], const float* __restrict__ bias, int n_first, int Cout, int act,
+                                         const float* __restrict__ slope = nullptr) {
     if (bias) {
         if (n_first + CH <= Cout && ((reinterpret_cast<uintptr_t>(bias + n_first) & 15) == 0)) {
 #pragma unroll
@@ -88,6 +90,10 @@ __device__ __forceinline__ void bias_act(float (&v)[CH], const float* __restrict
     } else if (act == 2) {
 #pragma unroll
         for (int j = 0; j < CH; ++j) v[j] = v[j] > 0.f ? v[j] : elu_neg(v[j]);
+    } else if (act == 3) {   // nn.PReLU(Cout) of the VFI network (IFRNet.py:121-125)
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+            if (n_first + j < Cout) v[j] = v[j] > 0.f ? v[j] : __ldg(slope + n_first + j) * v[j];
     }
 }
 
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
             float v[CH];
 #pragma unroll
             for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
-            bias_act<CH>(v, p.bias, n0 + c0, p.Cout, p.act);
+            bias_act<CH>(v, p.bias, n0 + c0, p.Cout, p.act, p.slope);
             if (vec_ok) {
 #pragma unroll
                 for (int j = 0; j < CH; j += 4)
@@ -379,16 +385,18 @@ __global__ void __launch_bounds__(NTHREADS) conv_dgrad_s2_kernel(const __grid_co
                 else tmem_ld16(taddr, r);
                 tmem_ld_wait();
                 if (!pix_ok || n0 + c0 >= p.Cout) continue;
+                float v[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+                bias_act<CH>(v, p.bias, n0 + c0, p.Cout, p.act, p.slope);   // transposed-convolution use: bias of nn.ConvTranspose2d
                 if (vec_ok) {
 #pragma unroll
                     for (int j = 0; j < CH; j += 4)
-                        if (n0 + c0 + j < p.Cout)
-                            *reinterpret_cast<float4*>(ypix + n0 + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                                        __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        if (n0 + c0 + j < p.Cout) *reinterpret_cast<float4*>(ypix + n0 + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 } else {
 #pragma unroll
                     for (int j = 0; j < CH; ++j)
-                        if (n0 + c0 + j < p.Cout) ypix[n0 + c0 + j] = __uint_as_float(r[j]);
+                        if (n0 + c0 + j < p.Cout) ypix[n0 + c0 + j] = v[j];
                 }
             }
             tc_fence_before();
@@ -418,6 +426,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_dgrad_s2_kernel(const __grid_co
 struct PatchArgs {
     float* y;
     const float* bias;
+    const float* slope;          // act == 3: per-channel PReLU slopes
     long long y_sB, y_sH, y_sW;
     int Cout, Ho, Wo;
     int KH, KW, pad;
@@ -606,7 +615,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
                     float v[SLAB];
 #pragma unroll
                     for (int jj = 0; jj < SLAB; ++jj) v[jj] = __uint_as_float(rr[jj]);
-                    bias_act<SLAB>(v, p.bias, n0 + c0, p.Cout, p.act);
+                    bias_act<SLAB>(v, p.bias, n0 + c0, p.Cout, p.act, p.slope);
                     if (use_tma) {
                         // the staging buffer must have been read by the TMA store issued two slabs ago
                         if (et == 0) tma_store_wait_read<1>();
@@ -771,7 +780,7 @@ static float* g_dbg = nullptr;
 void set_debug_buffer(float* p) { g_dbg = p; }
 
 static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const float* w_packed, const float* bias, float* y,
-                                      int act, cudaStream_t st, const char** why, EncodeTiledFn enc, int Ho, int Wo) {
+                                      int act, cudaStream_t st, const char** why, EncodeTiledFn enc, int Ho, int Wo, const float* slope) {
     int n_tile = 16;
     while (n_tile < d.Cout && n_tile < 128) n_tile *= 2;
     const int n_ntiles = (d.Cout + n_tile - 1) / n_tile;
@@ -793,7 +802,7 @@ static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const f
         return cudaErrorInvalidValue;
     }
     PatchArgs a;
-    a.y = y; a.bias = bias;
+    a.y = y; a.bias = bias; a.slope = slope;
     a.y_sB = d.y_sB; a.y_sH = d.y_sH; a.y_sW = d.y_sW;
     a.Cout = d.Cout; a.Ho = Ho; a.Wo = Wo; a.KH = d.KH; a.KW = d.KW; a.pad = d.pad;
     a.nseg = best_nseg;
@@ -890,8 +899,12 @@ static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const f
 }
 
 cudaError_t conv_forward(const ConvDesc& d, const float* x, const float* w_packed, const float* bias, float* y, int act,
-                         cudaStream_t st, const char** why) {
+                         cudaStream_t st, const char** why, const float* slope) {
     *why = nullptr;
+    if (act == 3 && !slope) {
+        *why = "PReLU epilogue needs the slope vector";
+        return cudaErrorInvalidValue;
+    }
     EncodeTiledFn enc = encode_fn();
     if (!enc) {
         *why = "cuTensorMapEncodeTiled is not available from the driver";
@@ -903,10 +916,11 @@ cudaError_t conv_forward(const ConvDesc& d, const float* x, const float* w_packe
     }
     const int Ho = out_size(d.H, d.KH, d.pad, d.stride), Wo = out_size(d.W, d.KW, d.pad, d.stride_x);
     if (d.stride == 1 && d.stride_x == 1 && d.KH * d.KW > 1 && d.KW <= 16 && !getenv("MVF_CONV_NO_PATCH"))
-        return conv_forward_patch(d, x, w_packed, bias, y, act, st, why, enc, Ho, Wo);
+        return conv_forward_patch(d, x, w_packed, bias, y, act, st, why, enc, Ho, Wo, slope);
     ConvArgs a;
     a.y = y;
     a.bias = bias;
+    a.slope = slope;
     a.y_sB = d.y_sB; a.y_sH = d.y_sH; a.y_sW = d.y_sW;
     a.Cout = d.Cout; a.Ho = Ho; a.Wo = Wo;
     a.KH = d.KH; a.KW = d.KW; a.pad = d.pad; a.stride = d.stride; a.stride_x = d.stride_x;
@@ -1011,7 +1025,8 @@ static cudaError_t launch_dgrad_s2(const CUtensorMap& mapA, const CUtensorMap& m
     return launch_pdl(conv_dgrad_s2_kernel<N_TILE>, dim3(ctas), dim3(NTHREADS), C::SMEM_BYTES, st, mapA, mapB, a, plan, n_mtiles, n_ntiles);
 }
 
-cudaError_t conv_dgrad_s2(const ConvDesc& d, const float* gy, const float* w_packed, float* gx, cudaStream_t st, const char** why) {
+cudaError_t conv_dgrad_s2(const ConvDesc& d, const float* gy, const float* w_packed, float* gx, cudaStream_t st, const char** why,
+                          const float* bias) {
     *why = conv_dgrad_s2_check(d);
     if (*why) return cudaErrorInvalidValue;
     EncodeTiledFn enc = encode_fn();
@@ -1029,7 +1044,8 @@ cudaError_t conv_dgrad_s2(const ConvDesc& d, const float* gy, const float* w_pac
     const int Hc = (d.H + 1) / 2, Wc = (d.W + 1) / 2;  // lattice of the largest class
     ConvArgs a = {};
     a.y = gx;
-    a.bias = nullptr;
+    a.bias = bias;   // non-null when the kernel serves as nn.ConvTranspose2d's forward (mvf_conv_transpose2d_s2_fwd)
+    a.slope = nullptr;
     a.y_sB = d.x_sB; a.y_sH = d.x_sH; a.y_sW = d.x_sW;
     a.Cout = d.Cin; a.Ho = d.H; a.Wo = d.W;
     a.KH = d.KH; a.KW = d.KW; a.pad = d.pad; a.stride = 1; a.stride_x = 1;

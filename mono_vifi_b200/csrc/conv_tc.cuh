@@ -33,11 +33,14 @@ cudaError_t umma_selftest(const float* A, const float* B, float* D, int N, int K
                           int row_off = 0, int base_off_mode = 0);
 void set_debug_buffer(float* p);  // development aid: dump of pipeline stage 0, see conv_tc.cu
 const char* conv_check(const ConvDesc& d);  // nullptr if the tcgen05 path covers the problem, else the reason
+// act: 0 none, 1 relu, 2 elu, 3 prelu with per-channel `slope`
 cudaError_t conv_forward(const ConvDesc& d, const float* x, const float* w_packed, const float* bias, float* y, int act,
-                         cudaStream_t st, const char** why);
+                         cudaStream_t st, const char** why, const float* slope = nullptr);
 // data gradient of a stride-2 convolution (d = the forward problem: x_* describe gx, y_* describe gy); see conv_tc.cu
 const char* conv_dgrad_s2_check(const ConvDesc& d);
-cudaError_t conv_dgrad_s2(const ConvDesc& d, const float* gy, const float* w_packed, float* gx, cudaStream_t st, const char** why);
+// (with `bias` it is the forward of nn.ConvTranspose2d(stride 2): the same arithmetic with the bias added in the epilogue)
+cudaError_t conv_dgrad_s2(const ConvDesc& d, const float* gy, const float* w_packed, float* gx, cudaStream_t st, const char** why,
+                          const float* bias = nullptr);
 int conv_dgrad_s2_plan_table(int KH, int KW, int pad, int* out, int capacity);
 
 }  // namespace tc

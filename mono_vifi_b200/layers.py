@@ -55,7 +55,11 @@ def disp_to_depth(disp, min_depth, max_depth):
 
 
 def transformation_from_parameters(axisangle, translation, invert=False):
-    """layers.py:28-45.  [B,1,3] x2 -> [B,4,4].  Twelve 4x4 matrices per step: stays torch."""
+    """layers.py:28-45.  [B,1,3] x2 -> [B,4,4].  On CUDA: one kernel forward, one backward (mvf_pose_matrix_*) instead of
+    the ~40 small launches of the op-by-op form below, which CPU tensors still take."""
+    if axisangle.is_cuda:
+        from . import warp_ops
+        return warp_ops.pose_matrix(axisangle, translation, invert)
     R = rot_from_axisangle(axisangle)
     t = translation.clone()
     if invert:
@@ -252,7 +256,10 @@ def upsample_fn(x):
 
 
 def upsample(x, scale_factor=2, mode="nearest"):
-    """layers.py:225-228"""
+    """layers.py:225-228 (mode="bilinear": the Lite-Mono decoder, LiteMono.py:495,502 -> mvf_resize_bilinear_* on CUDA)"""
+    if mode == "bilinear" and x.is_cuda:
+        from . import warp_ops
+        return warp_ops.resize_bilinear(x, scale_factor=scale_factor, align_corners=False)
     return F.interpolate(x, scale_factor=scale_factor, mode=mode)
 
 

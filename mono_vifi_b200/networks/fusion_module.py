@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import warp_ops
 from ..layers import ConvBlock1x1
 from .IFRNet import warp
 
@@ -39,7 +40,7 @@ class FusionModule(nn.Module):
         outs = []
         for i in range(len(self.num_ch_enc)):
             for _ in range(2 if (i == 0 and self.backbone == "LiteMono") else 1):
-                x = 0.5 * F.interpolate(x, scale_factor=0.5, mode="bilinear", align_corners=False)
+                x = warp_ops.resize_bilinear(x, scale_factor=0.5, mul=(0.5, 0.5))
             outs.append(fourier_embed(x, self.embed_multires))
         return outs
 
@@ -48,8 +49,7 @@ class FusionModule(nn.Module):
         outs = []
         for feat in features:
             H, W = feat.shape[-2:]
-            fl = F.interpolate(flow, size=(H, W), mode="bilinear", align_corners=False)
-            fl = fl * fl.new_tensor([W / fw, H / fh]).view(1, 2, 1, 1)
+            fl = warp_ops.resize_bilinear(flow, size=(H, W), mul=(W / fw, H / fh))
             outs.append(warp(feat, fl))
         return outs
 
@@ -57,7 +57,7 @@ class FusionModule(nn.Module):
         feats_n1, feats_0, feats_p1 = features_warped
         outs = []
         for f_n1, f_0, f_p1 in zip(feats_n1, feats_0, feats_p1):
-            m = F.interpolate(merge_mask, size=f_0.shape[-2:], mode="bilinear", align_corners=False)
+            m = warp_ops.resize_bilinear(merge_mask, size=f_0.shape[-2:])
             outs.append(torch.cat([f_0, m * f_n1 + (1 - m) * f_p1], 1))
         return outs
 

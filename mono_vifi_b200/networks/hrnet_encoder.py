@@ -6,6 +6,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import warp_ops
 from ..bn_act import bn_act
 from ..conv import Conv2d
 
@@ -115,7 +116,7 @@ class HighResolutionModule(nn.Module):
                 if j == i:
                     y = y + xs[j]
                 elif j > i:
-                    y = y + F.interpolate(row[j](xs[j]), size=xs[i].shape[-2:], mode="bilinear", align_corners=True)
+                    y = y + warp_ops.resize_bilinear(row[j](xs[j]), size=xs[i].shape[-2:], align_corners=True)
                 else:
                     y = y + row[j](xs[j])
             outs.append(self.relu(y))

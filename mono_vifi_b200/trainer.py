@@ -314,7 +314,9 @@ class TrainStep:
         else:
             out = single_frame_losses(self.models, inputs, self.opt, side=self.side, side2=self.side2)
         out["loss"].backward()
-        for st in (self.side, self.side2):  # parameter gradients of the pose branch were produced on the side streams
+        # parameter gradients of the pose branch were produced on the side streams (single-frame step only: a stream that took
+        # no part in the step must not be joined -- under graph capture that is a dependency on uncaptured work)
+        for st in (() if self.opt.multi_frame else (self.side, self.side2)):
             if st is not None:
                 torch.cuda.current_stream(self.device).wait_stream(st)
         if self.reducer is not None:
