@@ -54,6 +54,14 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, act=
             weight = F.pad(weight, (0, 0, 0, 0, 0, extra))
         if conv_tc.supported(x, weight, stride, padding, dilation, groups):
             stats["tcgen05"] += 1
+            cout = weight.shape[0]
+            if cout % 4 and cout > 4:
+                # HRNet-W18's 18-channel branch: zero output channels up to a 16-byte pixel, so that the backward's data /
+                # weight gradients stay on the tensor-core kernels too; the result is the leading-channel view
+                extra = 4 - cout % 4
+                weight = F.pad(weight, (0, 0, 0, 0, 0, 0, 0, extra))
+                bias = None if bias is None else F.pad(bias, (0, extra))
+                return conv_tc.conv2d(x, weight, bias, stride, padding, act=act)[:, :cout]
             return conv_tc.conv2d(x, weight, bias, stride, padding, act=act)
     stats["cudnn"] += 1
     return _activate(F.conv2d(x, weight, bias, stride, padding, dilation, groups), act)

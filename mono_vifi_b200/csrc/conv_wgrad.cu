@@ -43,6 +43,8 @@ struct WgradArgs {
     int pwx;           // shared patch: its pitch in pixels (pw + KW - 1)
     int stage_bytes, a_bytes, b_bytes;  // stage stride (1024-aligned), bytes landed for A and for B (all taps)
     int stages;        // pipeline depth (2..6), as many as fit in shared memory
+    int g_ragged;      // 1: Cout > 32 and not a multiple of 32 (HRNet's 36 / 72 / 144): mapG is the 4-D (co, ox, oy, b) map, one box per
+                       // 32-cout block, channels past Cout zero-filled by TMA
 };
 
 constexpr int MAX_STAGES = 6;
@@ -96,7 +98,12 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
                 unsigned char* st = smem + s * p.stage_bytes;
                 mbar_arrive_expect_tx(&full_bar[s], p.a_bytes + p.b_bytes);
                 // A: gy as (co%32, ox, oy, b, co/32), box (32, pw, ph, 1, 4) -> smem [co/32][pixel][32 co]
-                tma_load_5d(st, &mapG, &full_bar[s], 0, ox0, oy0, b, co0 / 32);
+                if (!p.g_ragged) {
+                    tma_load_5d(st, &mapG, &full_bar[s], 0, ox0, oy0, b, co0 / 32);
+                } else {
+                    for (int blk = 0; blk < M_TILE / 32; ++blk)   // same shared-memory layout; a block past Cout lands as zeros
+                        tma_load_4d(st + blk * (kp * 128), &mapG, &full_bar[s], co0 + 32 * blk, ox0, oy0, b);
+                }
                 if (p.shared_patch) {
                     // x as (ci, ix, iy, b), box (32, pw + KW - 1, KH, 1): the haloed patch all taps read
                     tma_load_4d(st + p.a_bytes, &mapX, &full_bar[s], ci0, ox0 - p.pad, oy0 - p.pad, b);
@@ -367,7 +374,6 @@ const char* wgrad_check(const WgradDesc& d) {
     if ((d.stride != 1 && d.stride != 2) || (d.stride_x != 1 && d.stride_x != 2)) return "strides must be 1 or 2";
     if (d.KH * d.KW > MAX_TAPS) return "more than 9 filter taps";
     if (d.Cin % 4 != 0 || d.Cout % 4 != 0) return "channel counts must be multiples of 4 (TMA: 16-byte pixels)";
-    if (d.Cout > 32 && d.Cout % 32 != 0) return "Cout above 32 must be a multiple of 32";
     if ((d.x_sH % 4) || (d.x_sW % 4) || (d.x_sB % 4) || (d.g_sH % 4) || (d.g_sW % 4) || (d.g_sB % 4))
         return "strides must be multiples of 4 elements (TMA: 16 bytes)";
     if (d.pad < 0 || d.H + 2 * d.pad < d.KH || d.W + 2 * d.pad < d.KW) return "bad padding";
@@ -412,7 +418,19 @@ cudaError_t conv_wgrad(const WgradDesc& d, const float* x, const float* gy, floa
     a.ksplit = pl.ksplit; a.cout_pad = pl.cout_pad; a.cin_pad = pl.cin_pad;
 
     CUtensorMap mapG, mapX;
-    {   // grad_out as (co%32, ox, oy, b, co/32)
+    a.g_ragged = (d.Cout > 32 && d.Cout % 32 != 0) ? 1 : 0;
+    if (a.g_ragged) {   // grad_out as (co, ox, oy, b): the kernel issues one box per 32-cout block
+        cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)pl.Wo, (cuuint64_t)pl.Ho, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)d.g_sW * 4, (cuuint64_t)d.g_sH * 4, (cuuint64_t)d.g_sB * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)PW, (cuuint32_t)PH, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        if (enc(&mapG, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(gy), dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            *why = "cuTensorMapEncodeTiled failed for grad_out";
+            return cudaErrorInvalidValue;
+        }
+    } else {   // grad_out as (co%32, ox, oy, b, co/32)
         const int c32 = d.Cout < 32 ? d.Cout : 32;
         cuuint64_t dims[5] = {(cuuint64_t)c32, (cuuint64_t)pl.Wo, (cuuint64_t)pl.Ho, (cuuint64_t)d.B, (cuuint64_t)((d.Cout + 31) / 32)};
         cuuint64_t strides[4] = {(cuuint64_t)d.g_sW * 4, (cuuint64_t)d.g_sH * 4, (cuuint64_t)d.g_sB * 4, 128};

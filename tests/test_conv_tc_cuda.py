@@ -146,6 +146,12 @@ WGRAD_CASES = [
     (2, 64, 10, 36, 32, 3, 0, 1),     # valid convolution
     (3, 256, 6, 20, 12, 1, 0, 1),     # pose head: 12 output channels
     (12, 64, 48, 160, 64, 3, 1, 1),   # ResNet layer1 at the benchmark size (split-K over 148 CTAs)
+    (2, 36, 24, 80, 36, 3, 1, 1),     # HRNet-W18 branch widths: Cout above 32 and not a multiple of 32 (per-block boxes, zero fill)
+    (2, 72, 12, 40, 72, 3, 1, 1),
+    (2, 144, 6, 20, 144, 3, 1, 1),
+    (2, 36, 24, 80, 72, 3, 1, 2),     # HRNet transition: stride 2, 36 -> 72
+    (2, 144, 6, 20, 36, 1, 0, 1),     # HRNet fuse layer: 1x1, 144 -> 36
+    (2, 20, 48, 160, 20, 3, 1, 1),    # the 18-channel branch as the layers run it (zero-padded to 20)
 ]
 
 
