@@ -224,6 +224,27 @@ int mvf_pose_matrix_fwd(const float* axisangle, const float* translation, float*
 int mvf_pose_matrix_bwd(const float* axisangle, const float* translation, const float* grad_M, float* grad_axisangle,
                         float* grad_translation, int B, int invert, void* stream);
 
+/* ---- Lite-Mono block kernels (csrc/litemono.cu); dense channels-last tensors [P pixels][C], C % 4 == 0 -------------------------
+ * mvf_dwconv3x3_*: depth-wise dilated 3x3 convolution, stride 1, zero padding = dilation (CDilated, networks/LiteMono.py:140-155,
+ *   called by DilatedConv.forward :179-201).  w_taps is the filter in tap-major order [9][C] (tap = kh*3 + kw); flip = 1 mirrors the
+ *   taps (= the data gradient: call it on grad_y).  wgrad writes grad_w in the module's [C,1,3,3] order; workspace:
+ *   mvf_dwconv3x3_wgrad_workspace_floats(P, C) floats; per-CTA partials added in a fixed order (reproducible).
+ * mvf_gelu_*: exact (erf) GELU of nn.GELU (LiteMono.py:127,172,216), backward from the saved input; n % 4 == 0.
+ * mvf_layernorm_cl_*: LayerNorm over C of channels-last tokens (LiteMono.py:93-121, data_format="channels_last"), eps inside the
+ *   square root; fwd keeps mean / rstd [P] for the backward; bwd gives grad_x, grad_weight, grad_bias (fixed-order partials).  C <= 512. */
+int mvf_dwconv3x3_fwd(const float* x, const float* w_taps, const float* bias, float* y, int B, int C, int H, int W, int dilation, int flip,
+                      void* stream);
+size_t mvf_dwconv3x3_wgrad_workspace_floats(long long P, int C);
+int mvf_dwconv3x3_wgrad(const float* x, const float* grad_y, float* grad_w, float* workspace, size_t workspace_floats, int B, int C, int H,
+                        int W, int dilation, void* stream);
+int mvf_gelu_fwd(const float* x, float* y, long long n, void* stream);
+int mvf_gelu_bwd(const float* x, const float* grad_y, float* grad_x, long long n, void* stream);
+int mvf_layernorm_cl_fwd(const float* x, const float* weight, const float* bias, float* y, float* mean, float* rstd, long long P, int C,
+                         float eps, void* stream);
+size_t mvf_layernorm_bwd_workspace_floats(long long P, int C);
+int mvf_layernorm_cl_bwd(const float* x, const float* grad_y, const float* weight, const float* mean, const float* rstd, float* grad_x,
+                         float* grad_weight, float* grad_bias, float* workspace, size_t workspace_floats, long long P, int C, void* stream);
+
 /* ---- fused training-mode BatchNorm2d (+ residual add) + ReLU on dense channels-last tensors [P pixels][C] -----------
  * The bn -> (+= identity) -> relu tail of torchvision's BasicBlock / Bottleneck (networks/monodepth2.py:16-31,
  * networks/posenet.py:10-52, hrnet_encoder.py:58-139).  fwd: batch statistics (biased variance for the normalisation),

@@ -74,6 +74,14 @@ SIGNATURES = {
     "mvf_prelu_cl_fwd": (_i, [_vp, _vp, _vp, _vp, ctypes.c_longlong, _i, _vp]),
     "mvf_pose_matrix_fwd": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "mvf_pose_matrix_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "mvf_dwconv3x3_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "mvf_dwconv3x3_wgrad_workspace_floats": (_sz, [ctypes.c_longlong, _i]),
+    "mvf_dwconv3x3_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
+    "mvf_gelu_fwd": (_i, [_vp, _vp, ctypes.c_longlong, _vp]),
+    "mvf_gelu_bwd": (_i, [_vp, _vp, _vp, ctypes.c_longlong, _vp]),
+    "mvf_layernorm_cl_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_longlong, _i, _f, _vp]),
+    "mvf_layernorm_bwd_workspace_floats": (_sz, [ctypes.c_longlong, _i]),
+    "mvf_layernorm_cl_bwd": (_i, [_vp] * 9 + [_sz, ctypes.c_longlong, _i, _vp]),
     "mvf_stream_capture_id": (ctypes.c_ulonglong, [_vp]),
     "mvf_conv2d_dgrad_s2_supported": (_i, [_CD]),
     "mvf_conv2d_dgrad_s2": (_i, [_CD, _vp, _vp, _vp, _vp]),

@@ -7,6 +7,7 @@
 #include "bn_cl.cuh"
 #include "conv_tc.cuh"
 #include "f1.cuh"
+#include "litemono.cuh"
 #include "ops.cuh"
 #include "ops_cl.cuh"
 #include "optim.cuh"
@@ -509,6 +510,44 @@ int mvf_pose_matrix_bwd(const float* axisangle, const float* translation, const 
         return fail(MVF_ERR_INVALID, "mvf_pose_matrix_bwd: bad argument");
     MVF_RUN("mvf_pose_matrix_bwd", mvf::pose_matrix_bwd(axisangle, translation, grad_M, grad_axisangle, grad_translation, B, invert,
                                                         (cudaStream_t)stream));
+}
+
+int mvf_dwconv3x3_fwd(const float* x, const float* w_taps, const float* bias, float* y, int B, int C, int H, int W, int dilation, int flip,
+                      void* stream) {
+    if (!x || !w_taps || !y || B <= 0 || C <= 0 || (C % 4) || H <= 0 || W <= 0 || dilation < 1)
+        return fail(MVF_ERR_INVALID, "mvf_dwconv3x3_fwd: bad argument (C % 4 == 0, dilation >= 1)");
+    MVF_RUN("mvf_dwconv3x3_fwd", mvf::dwconv3x3_fwd(x, w_taps, bias, y, B, C, H, W, dilation, flip, (cudaStream_t)stream));
+}
+size_t mvf_dwconv3x3_wgrad_workspace_floats(long long P, int C) { return (P > 0 && C > 0) ? mvf::dwconv3x3_wgrad_workspace_floats(P, C) : 0; }
+int mvf_dwconv3x3_wgrad(const float* x, const float* grad_y, float* grad_w, float* workspace, size_t workspace_floats, int B, int C, int H,
+                        int W, int dilation, void* stream) {
+    if (!x || !grad_y || !grad_w || !workspace || B <= 0 || C <= 0 || (C % 4) || C > 1024 || H <= 0 || W <= 0 || dilation < 1)
+        return fail(MVF_ERR_INVALID, "mvf_dwconv3x3_wgrad: bad argument (C % 4 == 0, C <= 1024)");
+    if (workspace_floats < mvf::dwconv3x3_wgrad_workspace_floats((long long)B * H * W, C)) return fail(MVF_ERR_INVALID, "mvf_dwconv3x3_wgrad: workspace too small");
+    MVF_RUN("mvf_dwconv3x3_wgrad", mvf::dwconv3x3_wgrad(x, grad_y, grad_w, workspace, B, C, H, W, dilation, (cudaStream_t)stream));
+}
+int mvf_gelu_fwd(const float* x, float* y, long long n, void* stream) {
+    if (!x || !y || n <= 0 || (n % 4)) return fail(MVF_ERR_INVALID, "mvf_gelu_fwd: bad argument (n % 4 == 0)");
+    MVF_RUN("mvf_gelu_fwd", mvf::gelu_fwd(x, y, n, (cudaStream_t)stream));
+}
+int mvf_gelu_bwd(const float* x, const float* grad_y, float* grad_x, long long n, void* stream) {
+    if (!x || !grad_y || !grad_x || n <= 0 || (n % 4)) return fail(MVF_ERR_INVALID, "mvf_gelu_bwd: bad argument (n % 4 == 0)");
+    MVF_RUN("mvf_gelu_bwd", mvf::gelu_bwd(x, grad_y, grad_x, n, (cudaStream_t)stream));
+}
+int mvf_layernorm_cl_fwd(const float* x, const float* weight, const float* bias, float* y, float* mean, float* rstd, long long P, int C,
+                         float eps, void* stream) {
+    if (!x || !weight || !bias || !y || !mean || !rstd || P <= 0 || C <= 0 || (C % 4) || C > 512)
+        return fail(MVF_ERR_INVALID, "mvf_layernorm_cl_fwd: bad argument (C % 4 == 0, C <= 512)");
+    MVF_RUN("mvf_layernorm_cl_fwd", mvf::layernorm_cl_fwd(x, weight, bias, y, mean, rstd, P, C, eps, (cudaStream_t)stream));
+}
+size_t mvf_layernorm_bwd_workspace_floats(long long P, int C) { return (P > 0 && C > 0) ? mvf::layernorm_bwd_workspace_floats(P, C) : 0; }
+int mvf_layernorm_cl_bwd(const float* x, const float* grad_y, const float* weight, const float* mean, const float* rstd, float* grad_x,
+                         float* grad_weight, float* grad_bias, float* workspace, size_t workspace_floats, long long P, int C, void* stream) {
+    if (!x || !grad_y || !weight || !mean || !rstd || !grad_x || !grad_weight || !grad_bias || !workspace || P <= 0 || C <= 0 || (C % 4) || C > 512)
+        return fail(MVF_ERR_INVALID, "mvf_layernorm_cl_bwd: bad argument (C % 4 == 0, C <= 512)");
+    if (workspace_floats < mvf::layernorm_bwd_workspace_floats(P, C)) return fail(MVF_ERR_INVALID, "mvf_layernorm_cl_bwd: workspace too small");
+    MVF_RUN("mvf_layernorm_cl_bwd", mvf::layernorm_cl_bwd(x, grad_y, weight, mean, rstd, grad_x, grad_weight, grad_bias, workspace, P, C,
+                                                           (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -10,7 +10,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..conv import Conv2d
+from .. import litemono_ops
+from ..bn_act import bn_act
+from ..conv import Conv2d, conv2d
 from ..layers import ConvBlock, Conv3x3, upsample
 
 
@@ -92,20 +94,27 @@ class LayerNorm(nn.Module):
 
     def forward(self, x):
         if self.data_format == "channels_last":
-            return F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)
+            return litemono_ops.layer_norm_cl(x, self.weight, self.bias, self.eps)   # mvf_layernorm_cl_* on CUDA
         u = x.mean(1, keepdim=True)
         s = (x - u).pow(2).mean(1, keepdim=True)
         return self.weight[:, None, None] * ((x - u) / torch.sqrt(s + self.eps)) + self.bias[:, None, None]
+
+
+class GELU(nn.GELU):
+    """nn.GELU() (erf form); mvf_gelu_* on CUDA"""
+
+    def forward(self, x):
+        return litemono_ops.gelu(x)
 
 
 class BNGELU(nn.Module):
     def __init__(self, nIn):
         super().__init__()
         self.bn = nn.BatchNorm2d(nIn, eps=1e-5)
-        self.act = nn.GELU()
+        self.act = GELU()
 
     def forward(self, x):
-        return self.act(self.bn(x))
+        return self.act(bn_act(self.bn, x, relu=False))
 
 
 class Conv(nn.Module):
@@ -127,7 +136,10 @@ class CDilated(nn.Module):
         self.conv = Conv2d(nIn, nOut, kSize, stride=stride, padding=int((kSize - 1) / 2) * d, bias=bias, dilation=d, groups=groups)
 
     def forward(self, x):
-        return self.conv(x)
+        c = self.conv
+        if litemono_ops.dwconv3x3_usable(x, c.weight, c.stride, c.padding, c.dilation, c.groups):
+            return litemono_ops.dwconv3x3(x, c.weight, c.bias, c.dilation)   # mvf_dwconv3x3_*
+        return c(x)
 
 
 class _Mlp(nn.Module):
@@ -136,6 +148,12 @@ class _Mlp(nn.Module):
     def _mlp(self, x):
         x = self.pwconv2(self.act(self.pwconv1(x)))
         return x if self.gamma is None else self.gamma * x
+
+    def _mlp_cl(self, x):
+        """the same on an NCHW-shaped channels-last tensor: the two nn.Linear layers are 1x1 convolutions on the tensor-core path"""
+        h = self.act(conv2d(x, self.pwconv1.weight[:, :, None, None], self.pwconv1.bias))
+        y = conv2d(h, self.pwconv2.weight[:, :, None, None], self.pwconv2.bias)
+        return y if self.gamma is None else y * self.gamma.view(1, -1, 1, 1)
 
 
 class DilatedConv(_Mlp):
@@ -147,12 +165,14 @@ class DilatedConv(_Mlp):
         self.bn1 = nn.BatchNorm2d(dim)
         self.norm = LayerNorm(dim, eps=1e-6)
         self.pwconv1 = nn.Linear(dim, expan_ratio * dim)
-        self.act = nn.GELU()
+        self.act = GELU()
         self.pwconv2 = nn.Linear(expan_ratio * dim, dim)
         self.gamma = nn.Parameter(layer_scale_init_value * torch.ones(dim)) if layer_scale_init_value > 0 else None
         self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
 
     def forward(self, x):
+        if x.is_cuda:
+            return x + self.drop_path(self._mlp_cl(bn_act(self.bn1, self.ddwconv(x), relu=False)))
         y = self.bn1(self.ddwconv(x)).permute(0, 2, 3, 1)
         return x + self.drop_path(self._mlp(y).permute(0, 3, 1, 2))
 
@@ -170,7 +190,7 @@ class LGFI(_Mlp):
         self.xca = XCA(dim, num_heads=num_heads, qkv_bias=qkv_bias, attn_drop=attn_drop, proj_drop=drop)
         self.norm = LayerNorm(dim, eps=1e-6)
         self.pwconv1 = nn.Linear(dim, expan_ratio * dim)
-        self.act = nn.GELU()
+        self.act = GELU()
         self.pwconv2 = nn.Linear(expan_ratio * dim, dim)
         self.gamma = nn.Parameter(layer_scale_init_value * torch.ones(dim)) if layer_scale_init_value > 0 else None
         self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
@@ -181,7 +201,10 @@ class LGFI(_Mlp):
         if self.pos_embd is not None:
             t = t + self.pos_embd(B, H, W).reshape(B, -1, t.shape[1]).permute(0, 2, 1)
         t = t + self.gamma_xca * self.xca(self.norm_xca(t))
-        y = self._mlp(self.norm(t.reshape(B, H, W, C))).permute(0, 3, 1, 2)
+        if x.is_cuda:
+            y = self._mlp_cl(self.norm(t.reshape(B, H, W, C)).permute(0, 3, 1, 2))
+        else:
+            y = self._mlp(self.norm(t.reshape(B, H, W, C))).permute(0, 3, 1, 2)
         return x + self.drop_path(y)
 
 
