@@ -170,6 +170,13 @@ size_t mvf_conv2d_wgrad_workspace_floats(const mvf_conv2d_desc* d);
 int mvf_conv2d_wgrad(const mvf_conv2d_desc* d, const float* x, const float* grad_out, float* grad_w, float* workspace,
                      size_t workspace_floats, void* stream);
 
+/* Packs every filter bank of a training step in ONE launch (instead of one mvf_conv2d_pack_filters launch per layer and direction:
+ * 155 per step of the ResNet18 configuration).  table (device memory): n_entries rows of 8 int64 {w pointer, out pointer, Cout, Cin,
+ * KH, KW, dgrad, first block}; bank e occupies blocks [first block_e, first block_e + ceil(packed floats_e / mvf_conv2d_pack_chunk())),
+ * total_blocks = their sum.  Same layouts as mvf_conv2d_pack_filters. */
+int mvf_conv2d_pack_chunk(void);
+int mvf_conv2d_pack_filters_multi(const long long* table, int n_entries, long long total_blocks, void* stream);
+
 /* Convolution + bias + nn.PReLU(Cout) in the epilogue: the `convrelu` block of the frozen VFI network (networks/IFRNet.py:121-125,
  * every encoder / decoder convolution of IFRNet.py:153-330).  Same descriptor / packed bank as mvf_conv2d_forward; slope[Cout]. */
 int mvf_conv2d_forward_prelu(const mvf_conv2d_desc* d, const float* x, const float* w_packed, const float* bias, const float* slope,

@@ -49,6 +49,8 @@ SIGNATURES = {
     "mvf_conv2d_pack_filters": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mvf_conv2d_supported": (_i, [_CD]),
     "mvf_conv2d_forward": (_i, [_CD, _vp, _vp, _vp, _vp, _i, _vp]),
+    "mvf_conv2d_pack_chunk": (_i, []),
+    "mvf_conv2d_pack_filters_multi": (_i, [_vp, _i, ctypes.c_longlong, _vp]),
     "mvf_conv2d_forward_prelu": (_i, [_CD, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvf_conv_transpose2d_s2_fwd": (_i, [_CD, _vp, _vp, _vp, _vp, _vp]),
     "mvf_conv2d_wgrad_supported": (_i, [_CD]),

@@ -91,7 +91,99 @@ weights_epoch = 0
 _pack_cache = {}
 
 
+class FilterBank:
+    """All filter banks of a training step packed by ONE kernel launch (mvf_conv2d_pack_filters_multi) at the start of the step,
+    instead of one launch per layer and direction inside the forward / backward (155 per step of the ResNet18 configuration).
+    `weights`: 4-D convolution weights and 2-D nn.Linear weights (used as 1x1 convolutions) that change every step;
+    `frozen`: weights of networks that are never trained (the VFI network) -- packed once, re-packed only if their version changes.
+    pack_filters() consults the active bank first; anything not registered (zero-padded or reshaped temporaries) is packed per call."""
+
+    def __init__(self, weights, frozen=()):
+        self._args = (list(weights), list(frozen))
+        self._build()
+
+    def _build(self):
+        """(re)build the pointer tables: the flat-arena optimiser re-points every parameter's storage at its first step"""
+        L = _lib.lib()
+        weights, frozen = self._args
+        self.chunk = L.mvf_conv2d_pack_chunk()
+        self.sets = []
+        self._ptrs = [w.data_ptr() for w in weights + frozen]
+        for ws, is_frozen in ((list(weights), False), (list(frozen), True)):
+            ws = [w for w in ws if w.is_cuda and w.dim() in (2, 4) and w.dtype == torch.float32 and w.is_contiguous()]
+            if not ws:
+                continue
+            shapes = [tuple(w.shape) if w.dim() == 4 else (w.shape[0], w.shape[1], 1, 1) for w in ws]
+            sizes = []
+            for (Cout, Cin, KH, KW) in shapes:
+                for dg in (0, 1):
+                    N, K = (Cin, Cout) if dg else (Cout, Cin)
+                    sizes.append(L.mvf_conv2d_packed_filter_floats(N, K, KH, KW))
+            arena = torch.empty(sum((n + 3) // 4 * 4 for n in sizes), device=ws[0].device, dtype=torch.float32)
+            rows, views, off, blk, j = [], {}, 0, 0, 0
+            for wi, (w, (Cout, Cin, KH, KW)) in enumerate(zip(ws, shapes)):
+                for dg in (0, 1):
+                    n = sizes[j]
+                    j += 1
+                    view = arena[off:off + n]
+                    rows.append([w.data_ptr(), view.data_ptr(), Cout, Cin, KH, KW, dg, blk])
+                    views[(w.data_ptr(), Cout, Cin, KH, KW, bool(dg))] = (view, wi)
+                    off += (n + 3) // 4 * 4
+                    blk += (n + self.chunk - 1) // self.chunk
+            self.sets.append({"frozen": is_frozen, "weights": ws, "arena": arena, "views": views, "blocks": blk, "n": len(rows),
+                              "table": torch.tensor(rows, dtype=torch.int64).to(ws[0].device), "tag": None, "versions": None})
+
+    def refresh(self):
+        """pack everything that may have changed; call at the start of a step, on the stream the step starts on"""
+        global _bank
+        L = _lib.lib()
+        if self._ptrs != [w.data_ptr() for w in self._args[0] + self._args[1]]:
+            self._build()
+        for st in self.sets:
+            dev = st["arena"].device
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            if st["frozen"]:
+                versions = [w._version for w in st["weights"]]
+                if st["versions"] == versions:
+                    continue
+                st["versions"] = versions
+            _lib.check(L.mvf_conv2d_pack_filters_multi(st["table"].data_ptr(), st["n"], st["blocks"], stream), "mvf_conv2d_pack_filters_multi")
+            launches["pack"] += 1
+            st["tag"] = (weights_epoch, L.mvf_stream_capture_id(stream), [w._version for w in st["weights"]])
+        _bank = self
+
+    def lookup(self, weight, dgrad):
+        Cout, Cin, KH, KW = weight.shape
+        key = (weight.data_ptr(), Cout, Cin, KH, KW, bool(dgrad))
+        for st in self.sets:
+            hit = st["views"].get(key)
+            if hit is None:
+                continue
+            view, wi = hit
+            tag = st["tag"]
+            if tag is None or tag[2][wi] != weight._version:   # (a view of a parameter shares its version counter)
+                return None
+            if st["frozen"]:
+                return view
+            if tag[0] == weights_epoch and tag[1] == _lib.lib().mvf_stream_capture_id(_stream(weight)):
+                return view
+            return None
+        return None
+
+    def release(self):
+        global _bank
+        if _bank is self:
+            _bank = None
+
+
+_bank = None
+
+
 def pack_filters(weight, dgrad=False):
+    if _bank is not None and weight.is_cuda:
+        hit = _bank.lookup(weight, dgrad)
+        if hit is not None:
+            return hit
     Cout, Cin, KH, KW = weight.shape
     N, K = (Cin, Cout) if dgrad else (Cout, Cin)
     key = tag = None

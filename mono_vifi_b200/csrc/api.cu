@@ -264,6 +264,11 @@ int mvf_conv2d_forward(const mvf_conv2d_desc* d, const float* x, const float* w_
     if (e != cudaSuccess) return why ? fail(MVF_ERR_CUDA, why) : fail(MVF_ERR_CUDA, "mvf_conv2d_forward launch", e);
     return MVF_OK;
 }
+int mvf_conv2d_pack_chunk(void) { return mvf::tc::pack_chunk(); }
+int mvf_conv2d_pack_filters_multi(const long long* table, int n_entries, long long total_blocks, void* stream) {
+    if (!table || n_entries <= 0 || total_blocks <= 0 || total_blocks > 0x7fffffffLL) return fail(MVF_ERR_INVALID, "mvf_conv2d_pack_filters_multi: bad argument");
+    MVF_RUN("mvf_conv2d_pack_filters_multi", mvf::tc::pack_filters_multi(table, n_entries, total_blocks, (cudaStream_t)stream));
+}
 int mvf_conv2d_forward_prelu(const mvf_conv2d_desc* d, const float* x, const float* w_packed, const float* bias, const float* slope,
                              float* y, void* stream) {
     if (!d || !x || !w_packed || !y || !slope) return fail(MVF_ERR_INVALID, "mvf_conv2d_forward_prelu: null pointer");

@@ -698,6 +698,47 @@ __global__ void pack_filters_kernel(const float* __restrict__ w, float* __restri
     }
 }
 
+// every filter bank of a step in ONE launch: table[e] = {w, out, Cout, Cin, KH, KW, dgrad, first block}; a CTA packs PACK_CHUNK
+// consecutive elements of one bank (entry found by binary search over the first-block column)
+constexpr int PACK_CHUNK = 2048;
+__global__ void __launch_bounds__(256) pack_filters_multi_kernel(const long long* __restrict__ table, int n_entries) {
+    int lo = 0, hi = n_entries - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (table[mid * 8 + 7] <= (long long)blockIdx.x) lo = mid;
+        else hi = mid - 1;
+    }
+    const long long* e = table + lo * 8;
+    const float* __restrict__ w = reinterpret_cast<const float*>(e[0]);
+    float* __restrict__ out = reinterpret_cast<float*>(e[1]);
+    const int Cout = (int)e[2], Cin = (int)e[3], KH = (int)e[4], KW = (int)e[5], dgrad = (int)e[6];
+    const int N = dgrad ? Cin : Cout, K = dgrad ? Cout : Cin;
+    const int ncb = (K + BLOCK_K - 1) / BLOCK_K;
+    const long long total = (long long)KH * KW * ncb * N * BLOCK_K;
+    const long long i0 = ((long long)blockIdx.x - e[7]) * PACK_CHUNK;
+    for (long long i = i0 + threadIdx.x; i < min(total, i0 + PACK_CHUNK); i += 256) {
+        const int kk = (int)(i % BLOCK_K);
+        long long r = i / BLOCK_K;
+        const int n = (int)(r % N);
+        r /= N;
+        const int cb = (int)(r % ncb);
+        const int tap = (int)(r / ncb);
+        const int k = cb * BLOCK_K + kk;
+        int kh = tap / KW, kw = tap - kh * KW;
+        float v = 0.f;
+        if (k < K) {
+            if (dgrad) {
+                kh = KH - 1 - kh;
+                kw = KW - 1 - kw;
+                v = w[(((long long)k * Cin + n) * KH + kh) * KW + kw];
+            } else {
+                v = w[(((long long)n * Cin + k) * KH + kh) * KW + kw];
+            }
+        }
+        out[i] = v;
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -761,6 +802,13 @@ cudaError_t pack_filters(const float* w, float* out, int Cout, int Cin, int KH, 
     const int threads = 256;
     const int blocks = (int)((total + threads - 1) / threads < 1184 ? (total + threads - 1) / threads : 1184);
     launch_pdl(pack_filters_kernel, dim3(blocks), dim3(threads), 0, st, w, out, Cout, Cin, KH, KW, dgrad);
+    return cudaGetLastError();
+}
+
+int pack_chunk() { return PACK_CHUNK; }
+cudaError_t pack_filters_multi(const long long* table, int n_entries, long long total_blocks, cudaStream_t st) {
+    if (total_blocks <= 0 || n_entries <= 0) return cudaSuccess;
+    pack_filters_multi_kernel<<<(unsigned)total_blocks, 256, 0, st>>>(table, n_entries);
     return cudaGetLastError();
 }
 

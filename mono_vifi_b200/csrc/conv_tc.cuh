@@ -29,6 +29,10 @@ cudaError_t conv_wgrad(const WgradDesc& d, const float* x, const float* gy, floa
 
 size_t packed_filter_floats(int N, int K, int KH, int KW);
 cudaError_t pack_filters(const float* w, float* out, int Cout, int Cin, int KH, int KW, int dgrad, cudaStream_t st);
+// all filter banks of a step in one launch; table (device): n_entries x {w, out, Cout, Cin, KH, KW, dgrad, first block} as int64,
+// every bank takes ceil(packed floats / pack_chunk()) blocks
+int pack_chunk();
+cudaError_t pack_filters_multi(const long long* table, int n_entries, long long total_blocks, cudaStream_t st);
 cudaError_t umma_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn_major, cudaStream_t st,
                           int row_off = 0, int base_off_mode = 0);
 void set_debug_buffer(float* p);  // development aid: dump of pipeline stage 0, see conv_tc.cu

@@ -214,62 +214,52 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
     }
 }
 
-// dw[co][ci][tap] = sum over splits (fixed order) of partial[split][tap][co][ci]; one thread = 4 consecutive cins
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin, int taps,
-                                    int ksplit, int cout_pad, int cin_pad) {
+// dw[co][ci][tap] = sum over splits of partial[split][tap][co][ci], in ONE fixed order (bitwise reproducible).
+// A CTA of 256 threads owns G = 256 / SL consecutive groups of 4 cins and SL "split lanes": thread (sl, g) adds splits sl, sl + SL, ...
+// of its group -- the G threads of one split lane read G * 16 contiguous bytes of one partial, so every sector is fully used and the
+// loads of a thread are independent (the round-1 kernels issued one dependent chain per output, or one warp per output whose lanes read
+// 32 different sectors: 42 us per launch on the narrow high-resolution layers) -- then the SL partial sums meet in shared memory and are
+// added in split-lane order.  SL is picked by the host so that narrow layers still fill the GPU.
+template <int SL>
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin,
+                                                           int taps, int ksplit, int cout_pad, int cin_pad) {
     pdl_sync();
+    constexpr int G = 256 / SL;
+    __shared__ float4 red[256];
     const int cin4 = (Cin + 3) / 4;
     const long long total = (long long)Cout * taps * cin4;
     const size_t split_stride = (size_t)taps * cout_pad * cin_pad;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c4 = (int)(i % cin4);
-        long long r = i / cin4;
-        const int t = (int)(r % taps);
-        const int co = (int)(r / taps);
-        const float4* src = reinterpret_cast<const float4*>(partial + ((size_t)t * cout_pad + co) * cin_pad + 4 * c4);
+    const int g = threadIdx.x % G, sl = threadIdx.x / G;
+    for (long long base = (long long)blockIdx.x * G; base < total; base += (long long)gridDim.x * G) {
+        const long long i = base + g;
+        const bool ok = i < total;
+        int c4 = 0, t = 0, co = 0;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < ksplit; ++s) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + s * split_stride));
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        if (ok) {
+            // groups are ordered (tap, cout, cin/4): consecutive groups are consecutive in the partial buffers
+            c4 = (int)(i % cin4);
+            const long long r = i / cin4;
+            co = (int)(r % Cout);
+            t = (int)(r / Cout);
+            const float* src = partial + ((size_t)t * cout_pad + co) * cin_pad + 4 * c4;
+#pragma unroll 4
+            for (int s = sl; s < ksplit; s += SL) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)s * split_stride));
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
         }
-        const int ci = 4 * c4;
-        float* o = dw + ((long long)co * Cin + ci) * taps + t;
-        o[0] = acc.x;
-        if (ci + 1 < Cin) o[taps] = acc.y;
-        if (ci + 2 < Cin) o[2 * taps] = acc.z;
-        if (ci + 3 < Cin) o[3 * taps] = acc.w;
-    }
-}
-
-// same reduction for many splits and few outputs (high-resolution, narrow layers): one WARP per group of 4 cins; lane l
-// adds splits l, l+32, ... and a fixed shuffle tree combines the lanes -- still one summation order, so deterministic
-__global__ void wgrad_reduce_warp_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin, int taps,
-                                         int ksplit, int cout_pad, int cin_pad) {
-    pdl_sync();
-    const int cin4 = (Cin + 3) / 4;
-    const long long total = (long long)Cout * taps * cin4;
-    const size_t split_stride = (size_t)taps * cout_pad * cin_pad;
-    const int lane = threadIdx.x & 31;
-    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long i = warp0; i < total; i += nwarps) {
-        const int c4 = (int)(i % cin4);
-        long long r = i / cin4;
-        const int t = (int)(r % taps);
-        const int co = (int)(r / taps);
-        const float* src = partial + ((size_t)t * cout_pad + co) * cin_pad + 4 * c4;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = lane; s < ksplit; s += 32) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(src + s * split_stride));
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        if (SL > 1) {
+            red[threadIdx.x] = acc;
+            __syncthreads();
+            if (sl == 0) {
+#pragma unroll 4
+                for (int q = 1; q < SL; ++q) {
+                    const float4 v = red[q * G + g];
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+            }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-            acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-        }
-        if (lane == 0) {
+        if (ok && sl == 0) {
             const int ci = 4 * c4;
             float* o = dw + ((long long)co * Cin + ci) * taps + t;
             o[0] = acc.x;
@@ -277,6 +267,7 @@ __global__ void wgrad_reduce_warp_kernel(const float* __restrict__ partial, floa
             if (ci + 2 < Cin) o[2 * taps] = acc.z;
             if (ci + 3 < Cin) o[3 * taps] = acc.w;
         }
+        if (SL > 1) __syncthreads();
     }
 }
 
@@ -471,17 +462,29 @@ cudaError_t conv_wgrad(const WgradDesc& d, const float* x, const float* gy, floa
     }
     e = launch_pdl(conv_wgrad_kernel, grid, dim3(NTHREADS), (size_t)smem, st, mapG, mapX, a);
     if (e != cudaSuccess) return e;
+    // split lanes: as few as keep ~2 CTAs per SM busy, but never more lanes than splits
     const long long total = (long long)d.Cout * taps * ((d.Cin + 3) / 4);
-    const int threads = 256;
-    if (pl.ksplit >= 16) {
-        const long long nb = (total + 7) / 8;  // 8 warps per block, one warp per output group
-        return launch_pdl(wgrad_reduce_warp_kernel, dim3((unsigned)(nb < 148 * 8 ? nb : 148 * 8)), dim3(threads), 0, st,
-                          (const float*)workspace, dw, d.Cout, d.Cin, taps, pl.ksplit, pl.cout_pad, pl.cin_pad);
-    } else {
-        const int blocks = (int)((total + threads - 1) / threads < 1184 ? (total + threads - 1) / threads : 1184);
-        return launch_pdl(wgrad_reduce_kernel, dim3(blocks), dim3(threads), 0, st, (const float*)workspace, dw, d.Cout, d.Cin, taps,
-                          pl.ksplit, pl.cout_pad, pl.cin_pad);
+    int sl = 1;
+    while (sl < 64 && sl * 2 <= pl.ksplit && total * sl / 256 < 2 * 148) sl *= 2;
+    const long long groups_per_cta = 256 / sl;
+    const long long nb = (total + groups_per_cta - 1) / groups_per_cta;
+    const dim3 rgrid((unsigned)(nb < 148 * 8 ? nb : 148 * 8));
+#define MVF_REDUCE(SLV)                                                                                                          \
+    case SLV:                                                                                                                    \
+        return launch_pdl(wgrad_reduce_kernel<SLV>, rgrid, dim3(256), 0, st, (const float*)workspace, dw, d.Cout, d.Cin, taps, pl.ksplit, \
+                          pl.cout_pad, pl.cin_pad)
+    switch (sl) {
+        MVF_REDUCE(1);
+        MVF_REDUCE(2);
+        MVF_REDUCE(4);
+        MVF_REDUCE(8);
+        MVF_REDUCE(16);
+        MVF_REDUCE(32);
+        default:
+            return launch_pdl(wgrad_reduce_kernel<64>, rgrid, dim3(256), 0, st, (const float*)workspace, dw, d.Cout, d.Cin, taps, pl.ksplit,
+                              pl.cout_pad, pl.cin_pad);
     }
+#undef MVF_REDUCE
     return cudaGetLastError();
 }
 

@@ -289,6 +289,22 @@ class TrainStep:
             # the shared pose weights receive gradients from two streams on purpose
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
 
+        # every filter bank of the step packed by one launch at its start (conv_tc.FilterBank); MVF_FILTER_BANK=0: per-layer packing
+        self.bank = None
+        if device.type == "cuda" and os.environ.get("MVF_FILTER_BANK", "1") != "0":
+            from . import conv, conv_tc
+            if conv.get_backend() == "tcgen05":
+                def conv_weights(mods):
+                    seen, out = set(), []
+                    for m in mods:
+                        for sub in m.modules():
+                            if isinstance(sub, (torch.nn.Conv2d, torch.nn.Linear)) and not isinstance(sub, torch.nn.ConvTranspose2d):
+                                if getattr(sub, "groups", 1) == 1 and id(sub.weight) not in seen:
+                                    seen.add(id(sub.weight))
+                                    out.append(sub.weight)
+                    return out
+                self.bank = conv_tc.FilterBank(conv_weights(self.models.values()), conv_weights([self.vfi]) if self.vfi is not None else ())
+
     def train(self):
         for m in self.models.values():
             m.train()
@@ -324,6 +340,8 @@ class TrainStep:
         return out
 
     def _step(self, inputs):
+        if self.bank is not None:
+            self.bank.refresh()
         out = self.forward_backward(inputs)
         if self.flat is not None:
             self.flat.step()  # all-reduce (N > 1) + clip + AdamW
