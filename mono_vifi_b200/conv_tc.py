@@ -22,7 +22,10 @@ timing = None
 _tag = "fprop"
 
 
-def _timed(tag, flops, fn):
+shapes = None   # a list: the (B, Cin, H, W, Cout, KH, KW, stride) of every timed launch, parallel to `timing` (tools/conv_layers.py)
+
+
+def _timed(tag, flops, fn, shape=None):
     if timing is None:
         return fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -30,6 +33,8 @@ def _timed(tag, flops, fn):
     r = fn()
     e1.record()
     timing.append((tag, flops, e0, e1))
+    if shapes is not None:
+        shapes.append(shape)
     return r
 
 
@@ -221,7 +226,8 @@ def conv_forward_raw(x, w_packed, bias, Cout, KH, KW, pad, stride=1, act=0, out=
     b = None if bias is None else bias.detach().float().contiguous()
     flops = 2.0 * B * Ho * Wo * Cout * Cin * KH * KW
     rc = _timed(_tag, flops, lambda: _lib.lib().mvf_conv2d_forward(
-        d, x.data_ptr(), w_packed.data_ptr(), None if b is None else b.data_ptr(), y.data_ptr(), act, _stream(x)))
+        d, x.data_ptr(), w_packed.data_ptr(), None if b is None else b.data_ptr(), y.data_ptr(), act, _stream(x)),
+        (B, Cin, H, W, Cout, KH, KW, stride))
     _lib.check(rc, "mvf_conv2d_forward")
     return y
 
@@ -403,7 +409,8 @@ def input_grad_s2(x, gy, weight, pad):
     Ho, Wo = gy.shape[2], gy.shape[3]
     flops = 2.0 * B * Ho * Wo * Cout * Cin * KH * KW
     _lib.check(_timed("dgrad", flops, lambda: _lib.lib().mvf_conv2d_dgrad_s2(d, gy.data_ptr(), pack_filters(weight, dgrad=True).data_ptr(),
-                                                                            gx.data_ptr(), _stream(gy))), "mvf_conv2d_dgrad_s2")
+                                                                            gx.data_ptr(), _stream(gy)), (B, Cin, H, W, Cout, KH, KW, 2)),
+               "mvf_conv2d_dgrad_s2")
     return gx
 
 
@@ -445,7 +452,8 @@ def weight_grad(x, gy, wshape, pad, stride=1):
         Ho, Wo = out_hw(H, W, KH, KW, pad, stride)
         flops = 2.0 * B * Ho * Wo * Cout * Cin * KH * KW
         _lib.check(_timed("wgrad", flops, lambda: L.mvf_conv2d_wgrad(d, x.data_ptr(), gy.data_ptr(), gw.data_ptr(), ws.data_ptr(),
-                                                                      ws.numel(), _stream(x))), "mvf_conv2d_wgrad")
+                                                                      ws.numel(), _stream(x)), (B, Cin, H, W, Cout, KH, KW, stride)),
+                   "mvf_conv2d_wgrad")
         return gw
     from . import conv
     conv.stats["cudnn_wgrad"] = conv.stats.get("cudnn_wgrad", 0) + 1

@@ -151,9 +151,13 @@ __device__ __forceinline__ float2 rep_window(const HS& a, const HS& b, const HS&
 // Barrier hand-offs: ONE arrival per warp (an mbarrier arrival per thread serialises 128-160 updates of one word per tile
 // and hand-off; measured 28 -> 20 us for the empty pipeline).  __syncwarp orders the other lanes' shared-memory accesses
 // before the arrival.  Waiting is done by the whole warp (a single-lane spin loop starved the working warps: 96 -> 160 us).
+#ifndef MVF_F1_SLEEP
+#define MVF_F1_SLEEP 0
+#endif
 __device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity, int lane) {
     (void)lane;
     while (!mbar_try_wait(bar, parity)) {   // whole warp: one broadcast request; the hardware suspends the warp inside try_wait
+        if (MVF_F1_SLEEP > 0) __nanosleep(MVF_F1_SLEEP);   // polling costs issue slots the working warps need
     }
 }
 __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
