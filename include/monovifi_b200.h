@@ -188,6 +188,19 @@ int mvf_conv2d_forward_prelu(const mvf_conv2d_desc* d, const float* x, const flo
  * mvf_conv2d_pack_filters(weight viewed as [Cin_t, Cout_t, k, k], dgrad = 1). */
 int mvf_conv_transpose2d_s2_fwd(const mvf_conv2d_desc* d, const float* x, const float* w_packed, const float* bias, float* y, void* stream);
 
+/* ---- SyncBatchNorm exchange over NVLink peer memory (csrc/peer.cu) ------------------------------------------------------------
+ * In-place SUM over all ranks of vec[n] (float64, n <= 2056: the [2C + 1] statistics vector of mvf_bn_sync_*), as ONE single-CTA kernel
+ * on `stream`: remote stores of this rank's vector into a slot of every rank's symmetric buffer, release / acquire flags carrying a
+ * sequence number, fixed rank-order sum (bitwise identical on every rank).  Replaces the per-call NCCL all-reduce of
+ * torch.nn.SyncBatchNorm (train.py:205-208).  peers_dev: device array of `world` pointers to the ranks' symmetric buffers
+ * (mvf_peer_buffer_bytes() bytes each, zero-initialised, e.g. torch.distributed._symmetric_memory); channel < 8: exchanges issued from
+ * different streams must use different channels; seq_local: this rank's 64-bit exchange counter of that channel (device memory,
+ * starts at 0, advanced by the kernel -- so CUDA-graph replays keep counting).  Every rank must issue the same exchanges in the same
+ * order per channel.  world <= 16. */
+size_t mvf_peer_buffer_bytes(void);
+int mvf_peer_allreduce_f64(double* vec, int n, void* const* peers_dev, int rank, int world, int channel, unsigned long long* seq_local,
+                           void* stream);
+
 /* ---- fused nearest-upsample x2 + channel concat + ReflectionPad2d(1), channels-last ---------------------------------
  * y[B,Ca+Cs,H+2,W+2] = pad(cat(upsample ? up2(a[B,Ca,H/2,W/2]) : a[B,Ca,H,W], skip[B,Cs,H,W])): the data movement
  * the reference does with F.interpolate + torch.cat + nn.ReflectionPad2d(1) before each decoder convolution

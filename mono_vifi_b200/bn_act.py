@@ -103,6 +103,18 @@ def group_for_stream(base_group, stream):
     return g
 
 
+def _exchange(sums, group, stream):
+    """cross-rank SUM of the statistics vector: one single-CTA kernel over NVLink peer memory (peer.py) when the node offers
+    symmetric memory, else an NCCL all-reduce on the stream's own communicator"""
+    import torch.distributed as dist
+    from . import peer
+    px = peer.get(group, sums.device)
+    if px is not None:
+        px.allreduce_(sums, stream)
+    else:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group_for_stream(group, stream))
+
+
 def _sync_world(bn):
     import torch.distributed as dist
     if not isinstance(bn, torch.nn.SyncBatchNorm) or not dist.is_available() or not dist.is_initialized():
@@ -131,7 +143,7 @@ class _BNActSync(torch.autograd.Function):
         launches["bn_fwd"] += 1
         launches["bn_sync"] = launches.get("bn_sync", 0) + 1
         _lib.check(L.mvf_bn_sync_stats_fwd(x.data_ptr(), sums.data_ptr(), ws.data_ptr(), ws.numel(), P, C, st), "mvf_bn_sync_stats_fwd")
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group_for_stream(group, cur))
+        _exchange(sums, group, cur)
         _lib.check(L.mvf_bn_sync_apply_fwd(x.data_ptr(), None if identity is None else identity.data_ptr(), y.data_ptr(),
                                            weight.data_ptr(), bias.data_ptr(), None if running_mean is None else running_mean.data_ptr(),
                                            None if running_var is None else running_var.data_ptr(),
@@ -163,7 +175,7 @@ class _BNActSync(torch.autograd.Function):
         _lib.check(L.mvf_bn_sync_stats_bwd(x.data_ptr(), gy.data_ptr(), y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), sums.data_ptr(),
                                            dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), ws.numel(), P, C, 1 if ctx.relu else 0, st),
                    "mvf_bn_sync_stats_bwd")
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group_for_stream(ctx.group, cur))
+        _exchange(sums, ctx.group, cur)
         _lib.check(L.mvf_bn_sync_apply_bwd(x.data_ptr(), gy.data_ptr(), y.data_ptr(), weight.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
                                            gx.data_ptr(), None if gid is None else gid.data_ptr(), sums.data_ptr(), scratch.data_ptr(),
                                            scratch.numel(), P, C, 1 if ctx.relu else 0, st), "mvf_bn_sync_apply_bwd")

@@ -11,6 +11,7 @@
 #include "ops.cuh"
 #include "ops_cl.cuh"
 #include "optim.cuh"
+#include "peer.cuh"
 #include "warp_cl.cuh"
 
 namespace {
@@ -553,6 +554,15 @@ int mvf_layernorm_cl_bwd(const float* x, const float* grad_y, const float* weigh
     if (workspace_floats < mvf::layernorm_bwd_workspace_floats(P, C)) return fail(MVF_ERR_INVALID, "mvf_layernorm_cl_bwd: workspace too small");
     MVF_RUN("mvf_layernorm_cl_bwd", mvf::layernorm_cl_bwd(x, grad_y, weight, mean, rstd, grad_x, grad_weight, grad_bias, workspace, P, C,
                                                            (cudaStream_t)stream));
+}
+
+size_t mvf_peer_buffer_bytes(void) { return mvf::peer_buffer_bytes(); }
+int mvf_peer_allreduce_f64(double* vec, int n, void* const* peers_dev, int rank, int world, int channel, unsigned long long* seq_local,
+                           void* stream) {
+    if (!vec || !peers_dev || !seq_local || n <= 0 || n > mvf::PEER_MAX_N || world < 1 || world > mvf::PEER_MAX_WORLD || rank < 0 ||
+        rank >= world || channel < 0 || channel >= mvf::PEER_CHANNELS)
+        return fail(MVF_ERR_INVALID, "mvf_peer_allreduce_f64: bad argument (n <= 2056, world <= 16, channel < 8)");
+    MVF_RUN("mvf_peer_allreduce_f64", mvf::peer_allreduce_f64(vec, n, peers_dev, rank, world, channel, seq_local, (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -14,7 +14,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from mono_vifi_b200 import conv_tc, ddp, trainer as TR  # noqa: E402
+from mono_vifi_b200 import conv_tc, ddp, peer, trainer as TR  # noqa: E402
 
 
 def main():
@@ -105,7 +105,8 @@ def main():
                           "grad_worst_rel": worst, "grad_worst_name": worst_name, "grad_rel_l2": (num / max(den, 1e-30)) ** 0.5,
                           "buffer_rel_err_vs_single": buf_err, "buffer_spread_across_ranks": buf_spread,
                           "loss_single": float(out_s["loss"]), "loss_dp_mean": float(loss_d),
-                          "weight_spread_after_step": w_spread}))
+                          "weight_spread_after_step": w_spread, "peer_exchanges": peer.exchanges,
+                          "exchange": "nvlink peer memory" if peer.exchanges else "nccl"}))
     dist.barrier()
     dist.destroy_process_group()
 

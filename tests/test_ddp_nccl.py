@@ -35,3 +35,5 @@ def test_data_parallel_step_equals_single_process_on_the_global_batch(mode):
     assert out["buffer_spread_across_ranks"] == 0.0, out       # identical bits on every rank
     assert abs(out["loss_single"] - out["loss_dp_mean"]) <= 1e-4 * abs(out["loss_single"]), out
     assert out["weight_spread_after_step"] == 0.0, out         # replicas stay bit-identical after the optimiser step
+    # the statistics exchange ran as the peer-memory kernel (two per SyncBatchNorm call), not as NCCL calls
+    assert out["peer_exchanges"] >= 2 * out["sync_bn_modules"], out
