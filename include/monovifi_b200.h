@@ -201,6 +201,19 @@ size_t mvf_peer_buffer_bytes(void);
 int mvf_peer_allreduce_f64(double* vec, int n, void* const* peers_dev, int rank, int world, int channel, unsigned long long* seq_local,
                            void* stream);
 
+/* ---- evaluation path (csrc/eval.cu; train.py:419-483 test_kitti, layers.py:293-311 compute_depth_errors) -----------------------
+ * mvf_bn_eval_fwd: y = relu?( BatchNorm2d_eval(x) + identity ) with the running statistics, dense channels-last [P][C], C % 4 == 0.
+ * mvf_depth_eval: one image -- disp[h,w] (the scaled disparity of disp_to_depth) is resized to the ground truth's [Hg,Wg]
+ *   (bilinear, align_corners=False), inverted to depth, masked (eigen_crop = 1: 1e-3 < gt < 80 inside the Eigen crop, = 0: gt > 0;
+ *   min_depth / max_depth are those two bounds), scaled by median(gt) / median(pred) (torch.median's lower median; stereo_scale > 0
+ *   uses that fixed factor instead), clamped to [min_depth, max_depth]; metrics8 = {abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3,
+ *   scale ratio}.  workspace: mvf_depth_eval_workspace_bytes(Hg, Wg) bytes, 16-byte aligned.  No host synchronisation. */
+int mvf_bn_eval_fwd(const float* x, const float* identity, float* y, const float* gamma, const float* beta, const float* running_mean,
+                    const float* running_var, long long P, int C, float eps, int relu, void* stream);
+size_t mvf_depth_eval_workspace_bytes(int Hg, int Wg);
+int mvf_depth_eval(const float* disp, int h, int w, const float* gt, int Hg, int Wg, float min_depth, float max_depth, int eigen_crop,
+                   float stereo_scale, void* workspace, size_t workspace_bytes, float* metrics8, void* stream);
+
 /* ---- fused nearest-upsample x2 + channel concat + ReflectionPad2d(1), channels-last ---------------------------------
  * y[B,Ca+Cs,H+2,W+2] = pad(cat(upsample ? up2(a[B,Ca,H/2,W/2]) : a[B,Ca,H,W], skip[B,Cs,H,W])): the data movement
  * the reference does with F.interpolate + torch.cat + nn.ReflectionPad2d(1) before each decoder convolution

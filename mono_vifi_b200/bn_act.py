@@ -244,6 +244,20 @@ def bn_act(bn, x, identity=None, relu=True):
         if world > 1:
             return _BNActSync.apply(x, identity, bn.weight, bn.bias, rm, rv, nbt, float(bn.eps), float(bn.momentum), bool(relu), group)
         return _BNAct.apply(x, identity, bn.weight, bn.bias, rm, rv, nbt, float(bn.eps), float(bn.momentum), bool(relu))
+    if (enabled and not bn.training and x.is_cuda and x.dim() == 4 and x.shape[1] % 4 == 0 and bn.affine and bn.track_running_stats and
+            x.dtype == torch.float32 and not (torch.is_grad_enabled() and (x.requires_grad or bn.weight.requires_grad))):
+        # inference (evaluation loop, train.py:419-483): running statistics, one pass (mvf_bn_eval_fwd)
+        x = _dense_cl(x)
+        B, C, H, W = x.shape
+        if identity is not None:
+            identity = _dense_cl(identity)
+        y = torch.empty(B, H, W, C, device=x.device, dtype=torch.float32).permute(0, 3, 1, 2)
+        launches["bn_eval"] = launches.get("bn_eval", 0) + 1
+        _lib.check(_lib.lib().mvf_bn_eval_fwd(x.data_ptr(), None if identity is None else identity.data_ptr(), y.data_ptr(),
+                                              bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                                              bn.running_var.data_ptr(), B * H * W, C, float(bn.eps), 1 if relu else 0,
+                                              torch.cuda.current_stream(x.device).cuda_stream), "mvf_bn_eval_fwd")
+        return y
     y = bn(x)
     if identity is not None:
         y = y + identity

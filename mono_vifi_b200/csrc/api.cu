@@ -6,6 +6,7 @@
 
 #include "bn_cl.cuh"
 #include "conv_tc.cuh"
+#include "eval.cuh"
 #include "f1.cuh"
 #include "litemono.cuh"
 #include "ops.cuh"
@@ -563,6 +564,22 @@ int mvf_peer_allreduce_f64(double* vec, int n, void* const* peers_dev, int rank,
         rank >= world || channel < 0 || channel >= mvf::PEER_CHANNELS)
         return fail(MVF_ERR_INVALID, "mvf_peer_allreduce_f64: bad argument (n <= 2056, world <= 16, channel < 8)");
     MVF_RUN("mvf_peer_allreduce_f64", mvf::peer_allreduce_f64(vec, n, peers_dev, rank, world, channel, seq_local, (cudaStream_t)stream));
+}
+
+int mvf_bn_eval_fwd(const float* x, const float* identity, float* y, const float* gamma, const float* beta, const float* running_mean,
+                    const float* running_var, long long P, int C, float eps, int relu, void* stream) {
+    if (!x || !y || !gamma || !beta || !running_mean || !running_var || P <= 0 || C <= 0 || (C % 4))
+        return fail(MVF_ERR_INVALID, "mvf_bn_eval_fwd: bad argument (C % 4 == 0)");
+    MVF_RUN("mvf_bn_eval_fwd", mvf::bn_eval_fwd(x, identity, y, gamma, beta, running_mean, running_var, P, C, eps, relu, (cudaStream_t)stream));
+}
+size_t mvf_depth_eval_workspace_bytes(int Hg, int Wg) { return (Hg > 0 && Wg > 0) ? mvf::depth_eval_workspace_bytes(Hg, Wg) : 0; }
+int mvf_depth_eval(const float* disp, int h, int w, const float* gt, int Hg, int Wg, float min_depth, float max_depth, int eigen_crop,
+                   float stereo_scale, void* workspace, size_t workspace_bytes, float* metrics8, void* stream) {
+    if (!disp || !gt || !workspace || !metrics8 || h <= 0 || w <= 0 || Hg <= 0 || Wg <= 0 || ((uintptr_t)workspace & 15))
+        return fail(MVF_ERR_INVALID, "mvf_depth_eval: bad argument");
+    if (workspace_bytes < mvf::depth_eval_workspace_bytes(Hg, Wg)) return fail(MVF_ERR_WORKSPACE, "mvf_depth_eval: workspace too small");
+    MVF_RUN("mvf_depth_eval", mvf::depth_eval(disp, h, w, gt, Hg, Wg, min_depth, max_depth, eigen_crop, stereo_scale, workspace, metrics8,
+                                              (cudaStream_t)stream));
 }
 
 }  // extern "C"
