@@ -4,6 +4,9 @@
 
   python bench.py --gpus N --steps K --warmup W            our arm (N>1: launched by torchrun, one rank per GPU)
   python bench.py --impl reference --gpus N ...            the reference path on the host CPU cores (rank 0 only)
+  python bench.py --impl torch-eager ...                   the same step on stock eager PyTorch / cuDNN on the GPU (informational)
+  python bench.py --config mf|3|4|5 ...                    the other BASELINE configurations (full multi-frame step; the default
+                                                           N=1 run of config 2 also reports them under "extra_configs")
 
 One JSON line on stdout (rank 0).  A "step" = zero_grad -> forward (2 pose nets, depth encoder + decoder, fused
 view synthesis + photometric loss) -> backward -> gradient all-reduce (N>1) -> clip -> AdamW, i.e. the single-frame
@@ -354,7 +357,7 @@ def run_ours(args):
 
     traffic = {}
     try:  # DRAM bytes per launch from the committed `ncu --set full` capture (only valid for the benchmark shape)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
     except Exception:
         pass
     std_shape = (args.batch, args.height, args.width) == (12, 192, 640)
@@ -366,10 +369,11 @@ def run_ours(args):
         avg_ms = sum(v) / len(v)
         ach = bpp * px / (avg_ms * 1e-3) / 1e9
         tr = traffic.get(tag + "_kernel", {}).get("dram_bytes_per_launch") if std_shape else None
-        return {"kernel": tag + "_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+        return {"kernel": (traffic.get(tag + "_kernel") or {}).get("kernel", tag + "_kernel") if std_shape else tag + "_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                 "traffic": tr, "avg_launch_us": avg_ms * 1e3, "launches_timed": len(v), "bytes_per_px": bpp,
                 "algorithmic_bytes_per_launch": bpp * px, "peak_source": peak_src,
-                "note": "instruction-issue bound (about 36 warp-instructions per pixel), see DESIGN.md section 4"}
+                "note": "instruction-issue / latency bound (about 23 useful warp-instructions per pixel), see DESIGN.md section 4 and "
+                        "profiles/r2_f1_ablation.md; traffic = dram__bytes of the committed ncu capture of this kernel and shape"}
     tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
     conv_roof = {}
     for tag, (fl, sec, n) in sorted(ct.items()):
