@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--cpu-batch", type=int, default=12, help="CPU arm: images per CPU step (the config's batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-fp32", action="store_true", help="e2e leg: feed the six fp32 tensors of the reference's loader instead of uint8 frames + GPU input pipeline")
     ap.add_argument("--torch-optimizer", action="store_true", help="torch clip_grad_norm_ + AdamW instead of the fused flat-arena kernels")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--conv-backend", default=os.environ.get("MVF_CONV_BACKEND", "tcgen05"), choices=["tcgen05", "cudnn"])
@@ -318,24 +319,52 @@ def run_ours(args):
     ms = e0.elapsed_time(e1) / args.steps
     my_launches = launches_per_step * args.steps
     # ---- timed region 2: end to end from pinned host memory -----------------------------------------------------
-    stage = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
+    # The host hands over what a loader produces after its resize: the item's three uint8 frames + the drawn augmentation
+    # parameters (+ K, inv_K); ToTensor / flip / ColorJitter run on the GPU (mono_vifi_b200/input_pipeline.py, mvf_input_pipeline)
+    # and write straight into the step's inputs.  --e2e-fp32 feeds the six fp32 tensors of the reference's loader instead.
+    import numpy as np
+    from mono_vifi_b200 import input_pipeline as IP
+    if args.e2e_fp32:
+        host_e2e = host
+    else:
+        host_e2e = []
+        for sidx in range(2):
+            rng = np.random.RandomState(1234 + 17 * rank + sidx)
+            pf, pi = IP.draw_params(args.batch, rng)
+            host_e2e.append({"frames_u8": torch.from_numpy(rng.randint(0, 256, (args.batch, 3, args.height, args.width, 3)).astype(np.uint8)).pin_memory(),
+                             "jitter_f": pf.pin_memory(), "jitter_i": pi.pin_memory(),
+                             ("K", 0): host[sidx][("K", 0)], ("inv_K", 0): host[sidx][("inv_K", 0)]})
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host_e2e[0].values())
+    stage = [{k: torch.empty_like(v, device=dev) for k, v in host_e2e[0].items()} for _ in range(2)]
+    eager_buf = {k: torch.empty_like(v, device=dev) for k, v in host[0].items()}
+    pipe = None if args.e2e_fp32 else IP.InputPipeline(args.batch, args.height, args.width, dev)
+    feeder = None
+    if run is not step:
+        feeder = TR.HostFedRunner(run, host[0]) if args.e2e_fp32 else IP.U8HostFedRunner(run, host_e2e[0])
+        feeder.feed(host_e2e[0])
+        feeder.run()                            # untimed: lazy initialisation of the feeding path
+        torch.cuda.synchronize()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    feeder = TR.HostFedRunner(run, host[0]) if run is not step else None
     e2.record()
     last = 0.0
     if feeder is not None:
-        feeder.feed(host[0])                    # inside the timed region: every step's H2D is
+        feeder.feed(host_e2e[0])                # inside the timed region: every step's H2D is
     for i in range(args.steps):
         if run is step:
             buf = stage[i % 2]
-            for k, v in host[i % 2].items():
+            for k, v in host_e2e[i % 2].items():
                 buf[k].copy_(v, non_blocking=True)
+            if pipe is not None:
+                pipe(buf["frames_u8"], buf["jitter_f"], buf["jitter_i"], out=eager_buf)
+                eager_buf[("K", 0)].copy_(buf[("K", 0)])
+                eager_buf[("inv_K", 0)].copy_(buf[("inv_K", 0)])
+                buf = eager_buf
             last = float(step(buf))  # D2H read of the step's loss
         else:
             loss_t = feeder.run()               # step i on the staged batch (graph replay)
             if i + 1 < args.steps:
-                feeder.feed(host[(i + 1) % 2])  # H2D of batch i+1 on the copy stream, overlapping step i
+                feeder.feed(host_e2e[(i + 1) % 2])  # H2D of batch i+1 on the copy stream, overlapping step i
             last = float(loss_t)                # D2H read of the step's loss (synchronises)
     e3.record()
     barrier()
@@ -394,7 +423,9 @@ def run_ours(args):
                        "conv_kernel_launches_per_step": conv_launches, "bn_calls_per_step": bn_calls,
                        "l2": "working set (activations, several GB) is far larger than the 126 MB L2; inputs rotate between two batches"},
             "e2e": {"value": args.batch * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "feed": ("six fp32 tensors per item (the reference loader's output)" if args.e2e_fp32 else
+                             "uint8 frames + augmentation parameters; ToTensor / flip / ColorJitter on the GPU (mvf_input_pipeline)")},
             "gpu_launches": my_launches, "clocks": clocks, "loss": last,
             "roofline": roof("f1_fwd", F1_FWD_BYTES_PER_PX), "roofline_bwd": roof("f1_bwd", F1_BWD_BYTES_PER_PX),
             "roofline_conv": conv_roof}

@@ -214,6 +214,19 @@ size_t mvf_depth_eval_workspace_bytes(int Hg, int Wg);
 int mvf_depth_eval(const float* disp, int h, int w, const float* gt, int Hg, int Wg, float min_depth, float max_depth, int eigen_crop,
                    float stereo_scale, void* workspace, size_t workspace_bytes, float* metrics8, void* stream);
 
+/* ---- GPU input pipeline (csrc/input.cu; datasets/mono_dataset.py:102-184, 206-238) ------------------------------------------------
+ * From a batch of uint8 frames already resized to the network resolution, frames[B, F, H, W, 3] (HWC), produce what
+ * MonoDataset.__getitem__ / preprocess hand to the trainer: color[f] = ToTensor(frame f) and color_aug[f] = ColorJitter(frame f),
+ * each fp32 [B, 3, H, W], with the item's horizontal flip applied to both (mono_dataset.py:224-226) and ONE jitter parameter set per
+ * item for all of its frames (mono_dataset.py:228-233).  prm_f[B,4] = brightness, contrast, saturation, hue factors;
+ * prm_i[B,6] = the order torchvision drew (4 entries: 0 brightness, 1 contrast, 2 saturation, 3 hue), do_color_aug, do_flip.
+ * color_dev / color_aug_dev: DEVICE arrays of F output pointers.  Arithmetic = torchvision's tensor kernels in fp32 (the reference's
+ * PIL path rounds to 8 bits after every operation: agreement to ~1/255 per operation).  workspace:
+ * mvf_input_pipeline_workspace_floats(B, F) floats.  A step's host-to-device copy shrinks from six fp32 tensors to the 8-bit frames. */
+size_t mvf_input_pipeline_workspace_floats(int B, int F);
+int mvf_input_pipeline(const unsigned char* frames, const float* prm_f, const int* prm_i, float* workspace, size_t workspace_floats,
+                       float* const* color_dev, float* const* color_aug_dev, int B, int F, int H, int W, void* stream);
+
 /* ---- fused nearest-upsample x2 + channel concat + ReflectionPad2d(1), channels-last ---------------------------------
  * y[B,Ca+Cs,H+2,W+2] = pad(cat(upsample ? up2(a[B,Ca,H/2,W/2]) : a[B,Ca,H,W], skip[B,Cs,H,W])): the data movement
  * the reference does with F.interpolate + torch.cat + nn.ReflectionPad2d(1) before each decoder convolution

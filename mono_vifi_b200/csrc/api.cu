@@ -8,6 +8,7 @@
 #include "conv_tc.cuh"
 #include "eval.cuh"
 #include "f1.cuh"
+#include "input.cuh"
 #include "litemono.cuh"
 #include "ops.cuh"
 #include "ops_cl.cuh"
@@ -580,6 +581,15 @@ int mvf_depth_eval(const float* disp, int h, int w, const float* gt, int Hg, int
     if (workspace_bytes < mvf::depth_eval_workspace_bytes(Hg, Wg)) return fail(MVF_ERR_WORKSPACE, "mvf_depth_eval: workspace too small");
     MVF_RUN("mvf_depth_eval", mvf::depth_eval(disp, h, w, gt, Hg, Wg, min_depth, max_depth, eigen_crop, stereo_scale, workspace, metrics8,
                                               (cudaStream_t)stream));
+}
+
+size_t mvf_input_pipeline_workspace_floats(int B, int F) { return (B > 0 && F > 0) ? mvf::input_pipeline_workspace_floats(B, F) : 0; }
+int mvf_input_pipeline(const unsigned char* frames, const float* prm_f, const int* prm_i, float* workspace, size_t workspace_floats,
+                       float* const* color_dev, float* const* color_aug_dev, int B, int F, int H, int W, void* stream) {
+    if (!frames || !prm_f || !prm_i || !workspace || !color_dev || !color_aug_dev || B <= 0 || F <= 0 || F > 16 || H <= 0 || W <= 0)
+        return fail(MVF_ERR_INVALID, "mvf_input_pipeline: bad argument");
+    if (workspace_floats < mvf::input_pipeline_workspace_floats(B, F)) return fail(MVF_ERR_WORKSPACE, "mvf_input_pipeline: workspace too small");
+    MVF_RUN("mvf_input_pipeline", mvf::input_pipeline(frames, prm_f, prm_i, workspace, color_dev, color_aug_dev, B, F, H, W, (cudaStream_t)stream));
 }
 
 }  // extern "C"
