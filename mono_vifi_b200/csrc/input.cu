@@ -4,7 +4,8 @@
 // hue in [-0.1, 0.1], in the random order torchvision draws) -- from the item's uint8 frames, so that a step's host-to-device
 // copy is the 8-bit frames (1.1 MB per sample at 192x640) instead of six fp32 tensors (8.8 MB).
 // Arithmetic: torchvision's tensor kernels (transforms/_functional_tensor.py: _blend, rgb_to_grayscale, _rgb2hsv, _hsv2rgb) in fp32;
-// the reference applies the PIL variants, which round to 8 bits after every operation, so outputs agree to ~1/255 per operation.
+// the reference applies the PIL variants, which round to 8 bits after every operation (~1/255 each) and convert to HSV in integers
+// (torchvision's own tensor and PIL backends differ by up to 9.6/255 in adjust_hue); parity is stated against the tensor backend.
 //   frames  uint8 [B, F, H, W, 3]  (HWC, what PIL / numpy hand over)      color, color_aug  fp32 [F][B, 3, H, W]
 //   prm_f   fp32 [B, 4] = brightness, contrast, saturation, hue factors    prm_i  int32 [B, 6] = order[4] (0 b, 1 c, 2 s, 3 h), do_aug, do_flip
 // Contrast needs the mean grey level of the WHOLE frame as it is when the operation runs; kernel 1 evaluates the chain up to that
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(NT) jitter_grey_partial_kernel(const unsigned 
     const unsigned char* src = frames + (size_t)bf * n * 3;
     float s = 0.f;
     for (long long i = i0 + threadIdx.x; i < i1; i += NT) {
-        float r = src[3 * i] * (1.f / 255.f), g = src[3 * i + 1] * (1.f / 255.f), bl = src[3 * i + 2] * (1.f / 255.f);
+        float r = __fdiv_rn((float)src[3 * i], 255.f), g = __fdiv_rn((float)src[3 * i + 1], 255.f), bl = __fdiv_rn((float)src[3 * i + 2], 255.f);
         chain(r, g, bl, order, f, n_before, 0.f);
         s += grey(r, g, bl);
     }
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(NT) input_pipeline_kernel(const unsigned char*
         const int* pi = prm_i + 6 * b;
         const int sx = pi[5] ? W - 1 - x : x;
         const unsigned char* src = frames + ((size_t)bf * n + (size_t)y * W + sx) * 3;
-        float r = src[0] * (1.f / 255.f), g = src[1] * (1.f / 255.f), bl = src[2] * (1.f / 255.f);
+        float r = __fdiv_rn((float)src[0], 255.f), g = __fdiv_rn((float)src[1], 255.f), bl = __fdiv_rn((float)src[2], 255.f);   // ToTensor: byte / 255, correctly rounded
         float* c = color[fr] + (size_t)b * 3 * n + p;
         c[0] = r; c[n] = g; c[2 * n] = bl;
         if (pi[4]) {
