@@ -298,7 +298,8 @@ int mvf_layernorm_cl_bwd(const float* x, const float* grad_y, const float* weigh
  * incremented on the device; pass NULL to skip), save_mean /
  * save_invstd [C] kept for the backward.  bwd: grad_x, grad_gamma, grad_beta and (optional) grad_identity = masked grad_y.
  * identity / y may be NULL (no residual / relu = 0).  workspace: mvf_bn_workspace_floats(P, C) floats of scratch; the
- * per-CTA partial sums are added in a fixed order (bitwise reproducible).  C % 4 == 0, C <= 1024. */
+ * per-CTA partial sums are added in a fixed order (bitwise reproducible).  C <= 1024; C % 4 == 0, or C % 4 == 2 with an even P (HRNet's
+ * 18-channel branch): two pixels are then processed as one row of 2C channels and save_mean / save_invstd must hold 2C floats. */
 size_t mvf_bn_workspace_floats(long long P, int C);
 int mvf_bn_relu_fwd(const float* x, const float* identity, float* y, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, long long* num_batches_tracked, float* save_mean, float* save_invstd, float* workspace,

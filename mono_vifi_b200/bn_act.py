@@ -45,8 +45,9 @@ class _BNAct(torch.autograd.Function):
         if identity is not None:
             identity = _dense_cl(identity)
         y = torch.empty(B, H, W, C, device=x.device, dtype=torch.float32).permute(0, 3, 1, 2)
-        mean = torch.empty(C, device=x.device, dtype=torch.float32)
-        invstd = torch.empty(C, device=x.device, dtype=torch.float32)
+        fold = 1 if C % 4 == 0 else 2     # C % 4 == 2 (HRNet's 18 channels): two pixels = one row of 2C channels, statistics kept per half
+        mean = torch.empty(fold * C, device=x.device, dtype=torch.float32)
+        invstd = torch.empty(fold * C, device=x.device, dtype=torch.float32)
         L = _lib.lib()
         ws = _workspace(x.device, L.mvf_bn_workspace_floats(P, C))
         st = torch.cuda.current_stream(x.device).cuda_stream
@@ -183,8 +184,14 @@ class _BNActSync(torch.autograd.Function):
 
 
 def usable(bn, x):
-    return (enabled and bn.training and x.is_cuda and x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[1] <= 1024 and
-            bn.affine and bn.momentum is not None and x.dtype == torch.float32)
+    if not (enabled and bn.training and x.is_cuda and x.dim() == 4 and x.shape[1] <= 1024 and bn.affine and bn.momentum is not None and
+            x.dtype == torch.float32):
+        return False
+    C = x.shape[1]
+    if C % 4 == 0:
+        return True
+    # C % 4 == 2: the single-process kernels fold two pixels into one row (the cross-rank SyncBatchNorm split does not)
+    return C % 2 == 0 and (x.shape[0] * x.shape[2] * x.shape[3]) % 2 == 0 and _sync_world(bn)[1] == 1
 
 
 # ---- deferred running statistics ------------------------------------------------------------------------------------

@@ -369,12 +369,13 @@ int mvf_maxpool3s2_bwd(const float* grad_y, const unsigned char* idx, float* gra
 }
 
 /* ---- fused BatchNorm2d (training) + residual add + ReLU, channels-last ------------------------------------------- */
-size_t mvf_bn_workspace_floats(long long P, int C) { return (P > 0 && C > 0 && C % 4 == 0 && C <= 1024) ? mvf::bn_workspace_floats(P, C) : 0; }
+static bool bn_shape_ok(long long P, int C) { return P > 0 && C > 0 && C <= 1024 && (C % 4 == 0 || (C % 2 == 0 && P % 2 == 0)); }
+size_t mvf_bn_workspace_floats(long long P, int C) { return bn_shape_ok(P, C) ? mvf::bn_workspace_floats(P, C) : 0; }
 int mvf_bn_relu_fwd(const float* x, const float* identity, float* y, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, long long* num_batches_tracked, float* save_mean, float* save_invstd, float* workspace,
                     size_t workspace_floats, long long P, int C, float eps, float momentum, int relu, void* stream) {
-    if (!x || !y || !gamma || !beta || !save_mean || !save_invstd || !workspace || P <= 0 || C <= 0 || (C % 4) || C > 1024)
-        return fail(MVF_ERR_INVALID, "mvf_bn_relu_fwd: bad argument (C % 4 == 0, C <= 1024)");
+    if (!x || !y || !gamma || !beta || !save_mean || !save_invstd || !workspace || !bn_shape_ok(P, C))
+        return fail(MVF_ERR_INVALID, "mvf_bn_relu_fwd: bad argument (C % 4 == 0, or C % 2 == 0 with an even pixel count; C <= 1024)");
     if (workspace_floats < mvf::bn_workspace_floats(P, C)) return fail(MVF_ERR_WORKSPACE, "mvf_bn_relu_fwd: workspace too small");
     MVF_RUN("mvf_bn_relu_fwd", mvf::bn_forward(x, identity, y, gamma, beta, running_mean, running_var, num_batches_tracked, save_mean, save_invstd, workspace,
                                                P, C, eps, momentum, relu, (cudaStream_t)stream));
@@ -382,9 +383,9 @@ int mvf_bn_relu_fwd(const float* x, const float* identity, float* y, const float
 int mvf_bn_relu_bwd(const float* x, const float* grad_y, const float* y, const float* gamma, const float* save_mean,
                     const float* save_invstd, float* grad_x, float* grad_identity, float* grad_gamma, float* grad_beta,
                     float* workspace, size_t workspace_floats, long long P, int C, int relu, void* stream) {
-    if (!x || !grad_y || !gamma || !save_mean || !save_invstd || !grad_x || !grad_gamma || !grad_beta || !workspace || P <= 0 ||
-        C <= 0 || (C % 4) || C > 1024 || (relu && !y))
-        return fail(MVF_ERR_INVALID, "mvf_bn_relu_bwd: bad argument (C % 4 == 0, C <= 1024)");
+    if (!x || !grad_y || !gamma || !save_mean || !save_invstd || !grad_x || !grad_gamma || !grad_beta || !workspace || !bn_shape_ok(P, C) ||
+        (relu && !y))
+        return fail(MVF_ERR_INVALID, "mvf_bn_relu_bwd: bad argument (C % 4 == 0, or C % 2 == 0 with an even pixel count; C <= 1024)");
     if (workspace_floats < mvf::bn_workspace_floats(P, C)) return fail(MVF_ERR_WORKSPACE, "mvf_bn_relu_bwd: workspace too small");
     MVF_RUN("mvf_bn_relu_bwd", mvf::bn_backward(x, grad_y, y, gamma, save_mean, save_invstd, grad_x, grad_identity, grad_gamma, grad_beta,
                                                 workspace, P, C, relu, (cudaStream_t)stream));

@@ -83,20 +83,28 @@ __global__ void __launch_bounds__(NT) bn_partial_kernel(const float4* __restrict
     }
 }
 
-// forward: mean / biased variance -> (mean, invstd) saved for backward, running statistics updated as nn.BatchNorm2d does
+// forward: mean / biased variance -> (mean, invstd) saved for backward, running statistics updated as nn.BatchNorm2d does.
+// fold > 1 (channel counts with C % 4 == 2, HRNet's 18): the tensor [P][C] is processed as [P / fold][fold * C] so that the float4
+// kernels apply; "virtual" channel j * C + c is real channel c at pixels of parity j.  The partial sums of the fold virtual channels of a
+// real channel are added here, mean / invstd (and copies of gamma / beta) are written for every virtual channel, the running
+// statistics once per real channel.  C is the REAL channel count, P the real pixel count.
 __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int nblocks, int C, long long P, float eps, float momentum,
                                        float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
-                                       float* __restrict__ running_var, long long* __restrict__ num_batches_tracked) {
+                                       float* __restrict__ running_var, long long* __restrict__ num_batches_tracked, int fold,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ gamma_v,
+                                       float* __restrict__ beta_v) {
     pdl_sync();
     if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
     // one warp per channel: lane l adds blocks l, l+32, ...; a fixed shuffle tree combines the lanes
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
+    const int Cv = fold * C;
     double s = 0.0, ss = 0.0;
-    for (int b = lane; b < nblocks; b += 32) {
-        s += (double)partial[(size_t)b * 2 * C + c];
-        ss += (double)partial[(size_t)b * 2 * C + C + c];
-    }
+    for (int b = lane; b < nblocks; b += 32)
+        for (int j = 0; j < fold; ++j) {
+            s += (double)partial[(size_t)b * 2 * Cv + j * C + c];
+            ss += (double)partial[(size_t)b * 2 * Cv + Cv + j * C + c];
+        }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -106,8 +114,14 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int nb
     const double m = s / (double)P;
     double var = ss / (double)P - m * m;
     if (var < 0.0) var = 0.0;
-    mean[c] = (float)m;
-    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    for (int j = 0; j < fold; ++j) {
+        mean[j * C + c] = (float)m;
+        invstd[j * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+        if (gamma_v) {
+            gamma_v[j * C + c] = gamma[c];
+            beta_v[j * C + c] = beta[c];
+        }
+    }
     if (running_mean) {
         const double unbiased = P > 1 ? var * (double)P / (double)(P - 1) : var;
         running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
@@ -115,17 +129,21 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int nb
     }
 }
 
-// backward: d_beta = sum g, d_gamma = sum g * xhat
+// backward: d_beta = sum g, d_gamma = sum g * xhat (fold: summed over the virtual channels of a real channel; per-virtual-channel
+// copies of d_gamma / d_beta / gamma for the apply kernel)
 __global__ void bn_finalize_bwd_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
+                                       float* __restrict__ dbeta, int fold, const float* __restrict__ gamma, float* __restrict__ dgamma_v,
+                                       float* __restrict__ dbeta_v, float* __restrict__ gamma_v) {
     pdl_sync();
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
+    const int Cv = fold * C;
     double s = 0.0, ss = 0.0;
-    for (int b = lane; b < nblocks; b += 32) {
-        s += (double)partial[(size_t)b * 2 * C + c];
-        ss += (double)partial[(size_t)b * 2 * C + C + c];
-    }
+    for (int b = lane; b < nblocks; b += 32)
+        for (int j = 0; j < fold; ++j) {
+            s += (double)partial[(size_t)b * 2 * Cv + j * C + c];
+            ss += (double)partial[(size_t)b * 2 * Cv + Cv + j * C + c];
+        }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -134,6 +152,12 @@ __global__ void bn_finalize_bwd_kernel(const float* __restrict__ partial, int nb
     if (lane != 0) return;
     dbeta[c] = (float)s;
     dgamma[c] = (float)ss;
+    if (dgamma_v)
+        for (int j = 0; j < fold; ++j) {
+            dgamma_v[j * C + c] = (float)ss;
+            dbeta_v[j * C + c] = (float)s;
+            gamma_v[j * C + c] = gamma[c];
+        }
 }
 
 __global__ void bn_apply_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ identity, float4* __restrict__ y,
@@ -354,34 +378,52 @@ int apply_blocks(long long total4) {
 
 }  // namespace
 
-size_t bn_workspace_floats(long long P, int C) { return (size_t)partial_blocks(P, C / 4) * 2 * C; }
+// C % 4 == 2 (and an even pixel count): two pixels are one row of 2C "virtual" channels
+static inline int fold_of(long long P, int C) { return (C % 4 == 0) ? 1 : 2; }
+
+size_t bn_workspace_floats(long long P, int C) {
+    const int fold = fold_of(P, C), Cv = fold * C;
+    return (size_t)partial_blocks(P / fold, Cv / 4) * 2 * Cv + (fold > 1 ? 4 * (size_t)Cv : 0);
+}
 
 cudaError_t bn_forward(const float* x, const float* identity, float* y, const float* gamma, const float* beta, float* running_mean,
                        float* running_var, long long* num_batches_tracked, float* save_mean, float* save_invstd, float* workspace,
                        long long P, int C, float eps, float momentum, int relu, cudaStream_t st) {
-    const int C4 = C / 4, nb = partial_blocks(P, C4);
+    // save_mean / save_invstd hold fold * C entries (the per-virtual-channel copies the backward kernels read)
+    const int fold = fold_of(P, C), Cv = fold * C, C4 = Cv / 4;
+    const long long Pv = P / fold;
+    const int nb = partial_blocks(Pv, C4);
     const int rows = NT / C4 > 0 ? NT / C4 : 1;
+    float* gamma_v = fold > 1 ? workspace + (size_t)nb * 2 * Cv : nullptr;
+    float* beta_v = fold > 1 ? gamma_v + Cv : nullptr;
     launch_pdl(bn_partial_kernel<false>, dim3((unsigned)(nb)), dim3(NT), (size_t)(2 * rows * C4 * sizeof(float4)), st, (const float4*)x, nullptr, nullptr, nullptr, nullptr,
-                                                                            workspace, P, C4, 0);
-    launch_pdl(bn_finalize_fwd_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), (size_t)(0), st, workspace, nb, C, P, eps, momentum, save_mean, save_invstd, running_mean,
-               running_var, num_batches_tracked);
-    const long long total4 = P * C4;
-    launch_pdl(bn_apply_fwd_kernel, dim3((unsigned)(apply_blocks(total4))), dim3(NT), (size_t)(0), st, (const float4*)x, (const float4*)identity, (float4*)y, save_mean,
-                                                           save_invstd, gamma, beta, total4, C4, relu);
+                                                                            workspace, Pv, C4, 0);
+    launch_pdl(bn_finalize_fwd_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), (size_t)(0), st, (const float*)workspace, nb, C, P, eps, momentum, save_mean, save_invstd,
+               running_mean, running_var, num_batches_tracked, fold, gamma, beta, gamma_v, beta_v);
+    const long long total4 = Pv * C4;
+    launch_pdl(bn_apply_fwd_kernel, dim3((unsigned)(apply_blocks(total4))), dim3(NT), (size_t)(0), st, (const float4*)x, (const float4*)identity, (float4*)y,
+               (const float*)save_mean, (const float*)save_invstd, fold > 1 ? (const float*)gamma_v : gamma, fold > 1 ? (const float*)beta_v : beta, total4, C4, relu);
     return cudaGetLastError();
 }
 
 cudaError_t bn_backward(const float* x, const float* gy, const float* y, const float* gamma, const float* save_mean,
                         const float* save_invstd, float* gx, float* gidentity, float* dgamma, float* dbeta, float* workspace,
                         long long P, int C, int relu, cudaStream_t st) {
-    const int C4 = C / 4, nb = partial_blocks(P, C4);
+    const int fold = fold_of(P, C), Cv = fold * C, C4 = Cv / 4;
+    const long long Pv = P / fold;
+    const int nb = partial_blocks(Pv, C4);
     const int rows = NT / C4 > 0 ? NT / C4 : 1;
+    float* dgamma_v = fold > 1 ? workspace + (size_t)nb * 2 * Cv : nullptr;
+    float* dbeta_v = fold > 1 ? dgamma_v + Cv : nullptr;
+    float* gamma_v = fold > 1 ? dbeta_v + Cv : nullptr;
     launch_pdl(bn_partial_kernel<true>, dim3((unsigned)(nb)), dim3(NT), (size_t)(2 * rows * C4 * sizeof(float4)), st, (const float4*)x, (const float4*)gy, (const float4*)y,
-                                                                           save_mean, save_invstd, workspace, P, C4, relu);
-    launch_pdl(bn_finalize_bwd_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), (size_t)(0), st, workspace, nb, C, dgamma, dbeta);
-    const long long total4 = P * C4;
+                                                                           save_mean, save_invstd, workspace, Pv, C4, relu);
+    launch_pdl(bn_finalize_bwd_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), (size_t)(0), st, (const float*)workspace, nb, C, dgamma, dbeta, fold, gamma, dgamma_v,
+               dbeta_v, gamma_v);
+    const long long total4 = Pv * C4;
     launch_pdl(bn_apply_bwd_kernel, dim3((unsigned)(apply_blocks(total4))), dim3(NT), (size_t)(0), st, (const float4*)x, (const float4*)gy, (const float4*)y, (float4*)gx,
-                                                           (float4*)gidentity, save_mean, save_invstd, gamma, dgamma, dbeta, total4,
+                                                           (float4*)gidentity, save_mean, save_invstd, fold > 1 ? (const float*)gamma_v : gamma,
+                                                           fold > 1 ? (const float*)dgamma_v : (const float*)dgamma, fold > 1 ? (const float*)dbeta_v : (const float*)dbeta, total4,
                                                            C4, (float)(1.0 / (double)P), relu);
     return cudaGetLastError();
 }

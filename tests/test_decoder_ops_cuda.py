@@ -73,7 +73,8 @@ def test_maxpool3s2_matches_torch(shape):
 
 
 @pytest.mark.parametrize("case", [(2, 64, 12, 20, True, True), (3, 128, 6, 10, False, True), (2, 16, 9, 7, True, False),
-                                  (12, 64, 96, 320, True, True), (1, 512, 6, 20, False, True), (2, 144, 6, 10, True, True)])
+                                  (12, 64, 96, 320, True, True), (1, 512, 6, 20, False, True), (2, 144, 6, 10, True, True),
+                                  (2, 18, 24, 40, True, True), (3, 18, 9, 14, False, False), (12, 18, 48, 160, True, True)])   # HRNet: C % 4 == 2
 def test_fused_bn_add_relu_matches_torch(case):
     """relu(bn(x) + identity) in training mode: output, running statistics and all gradients against torch in fp64"""
     import torch
