@@ -38,6 +38,72 @@ class FlatAdamW:
         self.params = None  # fixed after the first backward
         self._skip = None
         self._skip_key = None
+        # overlapped all-reduce (enable_overlap): buckets of the gradient arena are gathered and reduced on a communication stream
+        # as soon as autograd has produced all of their gradients, while the rest of the backward still runs
+        self._overlap = None
+
+    def enable_overlap(self, streams, n_buckets=6):
+        """streams: every CUDA stream the backward produces parameter gradients on (the reducer waits for them before it reads a
+        bucket).  Takes effect from the second step on (the arena layout is learnt in the first)."""
+        if self.distributed and dist.is_initialized() and dist.get_world_size() > 1:
+            self._overlap = {"streams": [s for s in streams if s is not None], "n": int(n_buckets), "ready": False}
+
+    def _setup_overlap(self):
+        ov = self._overlap
+        dev = self.P.device
+        ov["comm"] = torch.cuda.Stream(device=dev)
+        n = len(self.params)
+        target = max(1, self.n // ov["n"])
+        bounds, start, acc = [], 0, 0
+        for i in range(n):
+            acc += (self.sizes[i] + 3) // 4 * 4
+            if acc >= target and i + 1 < n:
+                bounds.append((start, i + 1))
+                start, acc = i + 1, 0
+        bounds.append((start, n))
+        ov["bounds"] = bounds
+        ov["bucket_of"] = [b for b, (lo, hi) in enumerate(bounds) for _ in range(lo, hi)]
+        ov["pending"] = [hi - lo for lo, hi in bounds]
+        ov["flushed"] = [False] * len(bounds)
+        ov["keep"] = []
+        for i, p in enumerate(self.params):
+            p.register_post_accumulate_grad_hook(lambda _p, i=i: self._on_grad(i))
+        ov["ready"] = True
+
+    def _on_grad(self, i):
+        ov = self._overlap
+        if ov is None or not ov["ready"] or not ov.get("armed", False):
+            return
+        b = ov["bucket_of"][i]
+        ov["pending"][b] -= 1
+        if ov["pending"][b] == 0 and not ov["flushed"][b]:
+            self._flush(b)
+
+    def _flush(self, b):
+        """gather bucket b's gradients into the arena and all-reduce that slice, on the communication stream"""
+        ov = self._overlap
+        lo, hi = ov["bounds"][b]
+        comm = ov["comm"]
+        cur = torch.cuda.current_stream(self.P.device)
+        comm.wait_stream(cur)
+        for s in ov["streams"]:
+            comm.wait_stream(s)
+        grads, ptrs = [], []
+        for p in self.params[lo:hi]:
+            g = p.grad
+            if g is not None and (g.dtype != torch.float32 or not g.is_contiguous()):
+                g = g.float().contiguous()
+            grads.append(g)
+            ptrs.append(None if g is None else g.data_ptr())
+        n = hi - lo
+        a0 = self.offs[lo]
+        a1 = self.offs[hi] if hi < len(self.params) else self.n
+        with torch.cuda.stream(comm):
+            _lib.check(_lib.lib().mvf_gather_grads(self.G.data_ptr(), (ctypes.c_void_p * n)(*ptrs), (ctypes.c_longlong * n)(*self.offs[lo:hi]),
+                                                   (ctypes.c_longlong * n)(*self.sizes[lo:hi]), n, comm.cuda_stream), "mvf_gather_grads")
+            dist.all_reduce(self.G[a0:a1], op=dist.ReduceOp.SUM)
+        ov["keep"].append(grads)    # temporaries stay alive until the step is over
+        ov["flushed"][b] = True
 
     # -- first step: find the parameters that got a gradient, build the arenas, adopt the gradients just computed
     def _build(self):
@@ -78,6 +144,14 @@ class FlatAdamW:
         """call before backward: with .grad None autograd adopts the tensors it computes instead of accumulating"""
         for p in (self.candidates if self.params is None else self.params):
             p.grad = None
+        ov = self._overlap
+        if ov is not None and self.params is not None:
+            if not ov["ready"]:
+                self._setup_overlap()
+            ov["pending"] = [hi - lo for lo, hi in ov["bounds"]]
+            ov["flushed"] = [False] * len(ov["bounds"])
+            ov["keep"] = []
+            ov["armed"] = True
 
     def _gather(self):
         grads, ptrs = [], []
@@ -91,6 +165,9 @@ class FlatAdamW:
         st = torch.cuda.current_stream(self.P.device).cuda_stream
         _lib.check(_lib.lib().mvf_gather_grads(self.G.data_ptr(), (ctypes.c_void_p * n)(*ptrs), self._c_offs, self._c_sizes, n, st),
                    "mvf_gather_grads")
+        self._update_skip(grads)
+
+    def _update_skip(self, grads):
         # parameters without a gradient this step are left untouched by the update (torch skips `grad is None`)
         missing = tuple(i for i, g in enumerate(grads) if g is None)
         if missing != self._skip_key:
@@ -106,9 +183,20 @@ class FlatAdamW:
     def step(self):
         if self.params is None:
             self._build()
-        self._gather()
-        if self.distributed and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.G, op=dist.ReduceOp.SUM)   # the 1 / world scale is applied inside the update kernel
+        ov = self._overlap
+        if ov is not None and ov["ready"] and ov.get("armed", False):
+            # buckets whose gradients all arrived were reduced during the backward; the rest (a parameter without a gradient this
+            # step keeps its bucket open) go now, then this stream joins the communication stream
+            for b in range(len(ov["bounds"])):
+                if not ov["flushed"][b]:
+                    self._flush(b)
+            torch.cuda.current_stream(self.P.device).wait_stream(ov["comm"])
+            ov["armed"] = False
+            self._update_skip([p.grad for p in self.params])
+        else:
+            self._gather()
+            if self.distributed and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(self.G, op=dist.ReduceOp.SUM)   # the 1 / world scale is applied inside the update kernel
         st = torch.cuda.current_stream(self.P.device).cuda_stream
         from . import conv_tc
         conv_tc.weights_epoch += 1  # the parameters change underneath their tensors' version counters

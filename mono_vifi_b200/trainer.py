@@ -285,6 +285,10 @@ class TrainStep:
                      if device.type == "cuda" and os.environ.get("MVF_SIDE_STREAM", "2") != "0" else None)
         self.side2 = (torch.cuda.Stream(device=device)
                       if self.side is not None and os.environ.get("MVF_SIDE_STREAM", "2") == "2" else None)
+        if self.flat is not None and distributed and os.environ.get("MVF_OVERLAP_ALLREDUCE", "0") != "0":
+            # MVF_OVERLAP_ALLREDUCE=<buckets>: the gradient arena is reduced bucket by bucket on a communication stream while the
+            # backward still runs (optim.FlatAdamW.enable_overlap).  Off by default: see DESIGN.md section 5 for the measurement.
+            self.flat.enable_overlap([self.stream, self.side, self.side2], n_buckets=max(2, int(os.environ["MVF_OVERLAP_ALLREDUCE"])))
         if self.side2 is not None and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
             # the shared pose weights receive gradients from two streams on purpose
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)

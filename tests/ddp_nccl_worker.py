@@ -93,6 +93,21 @@ def main():
     with torch.cuda.stream(step_d.stream):
         step_d.flat.step()
     torch.cuda.synchronize()
+    # ---- a second, complete step on both sides: the data-parallel one now reduces its gradient buckets on the communication
+    # stream during the backward (FlatAdamW.enable_overlap takes effect once the arena exists) ----
+    with torch.cuda.stream(step_s.stream):
+        step_s.flat.step()
+        step_s._step(inputs_g)
+    with torch.cuda.stream(step_d.stream):
+        step_d._step(inputs_l)
+    torch.cuda.synchronize()
+    ov = step_d.flat._overlap
+    buckets_overlapped = 0 if ov is None else len(ov["bounds"])
+    # the reduced gradient arena of the second step (sum over ranks; the 1 / world scale lives in the AdamW kernel) against the single
+    # process's arena.  (Weights themselves are a poor yardstick: Adam's first steps move every weight by ~lr whatever the size of its
+    # gradient, so parameters with noise-level gradients differ by whole updates between any two runs.)
+    gs, gd = step_s.flat.G.double(), step_d.flat.G.double() / world
+    w_err_rel = float((gs - gd).norm() / gs.norm()) if gs.numel() == gd.numel() else float("nan")
     w_spread = 0.0
     for m in m_d.values():
         for p in m.parameters():
@@ -106,6 +121,7 @@ def main():
                           "buffer_rel_err_vs_single": buf_err, "buffer_spread_across_ranks": buf_spread,
                           "loss_single": float(out_s["loss"]), "loss_dp_mean": float(loss_d),
                           "weight_spread_after_step": w_spread, "peer_exchanges": peer.exchanges,
+                          "allreduce_buckets_overlapped": buckets_overlapped, "second_step_reduced_grad_rel_l2": w_err_rel,
                           "exchange": "nvlink peer memory" if peer.exchanges else "nccl"}))
     dist.barrier()
     dist.destroy_process_group()
