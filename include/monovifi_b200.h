@@ -227,6 +227,17 @@ size_t mvf_input_pipeline_workspace_floats(int B, int F);
 int mvf_input_pipeline(const unsigned char* frames, const float* prm_f, const int* prm_i, float* workspace, size_t workspace_floats,
                        float* const* color_dev, float* const* color_aug_dev, int B, int F, int H, int W, void* stream);
 
+/* ---- disparity head (csrc/dispconv.cu): Conv3x3(C, 1) on the padded channels-last decoder feature (networks/monodepth2.py:76-77, 94;
+ * LiteMono.py:468-469, 502).  xp: dense channels-last [B, H+2, W+2, C] (the reflection-padded input of mvf_upcat_pad_fwd), C % 4 == 0,
+ * C <= 64; w: the module's [1, C, 3, 3] weight; y / grad_y: [B, H, W].  HBM-bound direct kernels instead of an N = 16 tensor-core
+ * tile with 15 zero columns.  wgrad also returns the bias gradient (grad_b may be NULL); workspace:
+ * mvf_dispconv_wgrad_workspace_floats(B*H*W, C) floats, partials added in a fixed order. */
+int mvf_dispconv_fwd(const float* xp, const float* w, const float* bias, float* y, int B, int C, int H, int W, void* stream);
+int mvf_dispconv_dgrad(const float* grad_y, const float* w, float* grad_xp, int B, int C, int H, int W, void* stream);
+size_t mvf_dispconv_wgrad_workspace_floats(long long P, int C);
+int mvf_dispconv_wgrad(const float* xp, const float* grad_y, float* grad_w, float* grad_b, float* workspace, size_t workspace_floats, int B,
+                       int C, int H, int W, void* stream);
+
 /* ---- fused nearest-upsample x2 + channel concat + ReflectionPad2d(1), channels-last ---------------------------------
  * y[B,Ca+Cs,H+2,W+2] = pad(cat(upsample ? up2(a[B,Ca,H/2,W/2]) : a[B,Ca,H,W], skip[B,Cs,H,W])): the data movement
  * the reference does with F.interpolate + torch.cat + nn.ReflectionPad2d(1) before each decoder convolution

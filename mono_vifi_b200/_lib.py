@@ -91,6 +91,10 @@ SIGNATURES = {
     "mvf_depth_eval": (_i, [_vp, _i, _i, _vp, _i, _i, _f, _f, _i, _f, _vp, _sz, _vp, _vp]),
     "mvf_input_pipeline_workspace_floats": (_sz, [_i, _i]),
     "mvf_input_pipeline": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "mvf_dispconv_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "mvf_dispconv_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "mvf_dispconv_wgrad_workspace_floats": (_sz, [ctypes.c_longlong, _i]),
+    "mvf_dispconv_wgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp]),
     "mvf_stream_capture_id": (ctypes.c_ulonglong, [_vp]),
     "mvf_conv2d_dgrad_s2_supported": (_i, [_CD]),
     "mvf_conv2d_dgrad_s2": (_i, [_CD, _vp, _vp, _vp, _vp]),

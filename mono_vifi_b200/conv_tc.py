@@ -550,11 +550,87 @@ class _Conv2dTC3x(torch.autograd.Function):
         return gx, gw, gb, None, None
 
 
+# ---- disparity head: Conv3x3(C, 1) on the padded decoder feature (csrc/dispconv.cu) -- an HBM-bound direct kernel in fp32 instead
+# of an N = 16 tensor-core tile with 15 zero columns (and a zero-padded 4-channel copy of grad_out for its data gradient)
+dispconv_enabled = os.environ.get("MVF_DISPCONV", "1") != "0"
+_disp_ws = {}
+
+
+def dispconv_supported(x, weight, stride, pad):
+    Cout, Cin, KH, KW = weight.shape
+    return (dispconv_enabled and x.is_cuda and Cout == 1 and (KH, KW) == (3, 3) and pad == 0 and _pair(stride) == (1, 1)
+            and Cin % 4 == 0 and Cin <= 64 and x.shape[1] == Cin and x.shape[2] >= 3 and x.shape[3] >= 3)
+
+
+class _DispConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xp, weight, bias):
+        xp = _as_input(xp)
+        if not _dense_cl(xp):
+            xp = xp.contiguous(memory_format=torch.channels_last)
+        B, C, Hp, Wp = xp.shape
+        H, W = Hp - 2, Wp - 2
+        launches["fprop"] += 1
+        y = torch.empty(B, 1, H, W, device=xp.device, dtype=torch.float32)
+        w = weight.detach().contiguous()
+        _timed("fprop", 2.0 * B * H * W * C * 9, lambda: _lib.check(_lib.lib().mvf_dispconv_fwd(
+            xp.data_ptr(), w.data_ptr(), None if bias is None else bias.data_ptr(), y.data_ptr(), B, C, H, W, _stream(xp)),
+            "mvf_dispconv_fwd"), (B, C, Hp, Wp, 1, 3, 3, 1))
+        ctx.save_for_backward(xp, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xp, weight = ctx.saved_tensors
+        B, C, Hp, Wp = xp.shape
+        H, W = Hp - 2, Wp - 2
+        gy = gy.contiguous().float()
+        L = _lib.lib()
+        gx = gw = gb = None
+
+        def wgrad():
+            launches["wgrad"] += 1
+            n = L.mvf_dispconv_wgrad_workspace_floats(B * H * W, C)
+            key = (gy.device.index, _stream(gy))
+            ws = _disp_ws.get(key)
+            if ws is None or ws.numel() < n:
+                ws = _disp_ws[key] = torch.empty(n, device=gy.device, dtype=torch.float32)
+            g_w = torch.empty(1, C, 3, 3, device=gy.device, dtype=torch.float32)
+            g_b = torch.empty(1, device=gy.device, dtype=torch.float32) if ctx.has_bias and ctx.needs_input_grad[2] else None
+            _timed("wgrad", 2.0 * B * H * W * C * 9, lambda: _lib.check(L.mvf_dispconv_wgrad(
+                xp.data_ptr(), gy.data_ptr(), g_w.data_ptr(), None if g_b is None else g_b.data_ptr(), ws.data_ptr(), ws.numel(),
+                B, C, H, W, _stream(gy)), "mvf_dispconv_wgrad"), (B, C, Hp, Wp, 1, 3, 3, 1))
+            return g_w, g_b
+
+        fork = None
+        if ctx.needs_input_grad[1] and ctx.needs_input_grad[0] and wgrad_stream_enabled and timing is None:
+            cur = torch.cuda.current_stream(gy.device)
+            fork = _companion(cur)
+            fork.wait_stream(cur)
+            with torch.cuda.stream(fork):
+                gw, gb = wgrad()
+        if ctx.needs_input_grad[0]:
+            launches["dgrad"] += 1
+            gx = torch.empty(B, Hp, Wp, C, device=gy.device, dtype=torch.float32).permute(0, 3, 1, 2)
+            w = weight.detach().contiguous()
+            _timed("dgrad", 2.0 * B * H * W * C * 9, lambda: _lib.check(L.mvf_dispconv_dgrad(
+                gy.data_ptr(), w.data_ptr(), gx.data_ptr(), B, C, H, W, _stream(gy)), "mvf_dispconv_dgrad"),
+                (B, 1, H, W, C, 3, 3, 1))
+        if fork is not None:
+            cur.wait_stream(fork)
+        elif ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gw, gb = wgrad()
+        return gx, gw, gb
+
+
 def conv2d(x, weight, bias=None, stride=1, padding=0, act=None):
     """act: None | "relu" | "elu" -- applied in the kernel's epilogue (its backward uses the saved output)."""
     pad = padding if isinstance(padding, int) else padding[0]
     st = _pair(stride)
     st = st[0] if st[0] == st[1] else st
+    if act is None and dispconv_supported(x, weight, st, pad):
+        return _DispConv.apply(x, weight, bias)      # fp32 arithmetic in either precision mode
     if _precision == "3xtf32":
         y = _Conv2dTC3x.apply(x, weight, bias, pad, st)
         if act == "relu":

@@ -6,6 +6,7 @@
 
 #include "bn_cl.cuh"
 #include "conv_tc.cuh"
+#include "dispconv.cuh"
 #include "eval.cuh"
 #include "f1.cuh"
 #include "input.cuh"
@@ -591,6 +592,23 @@ int mvf_input_pipeline(const unsigned char* frames, const float* prm_f, const in
         return fail(MVF_ERR_INVALID, "mvf_input_pipeline: bad argument");
     if (workspace_floats < mvf::input_pipeline_workspace_floats(B, F)) return fail(MVF_ERR_WORKSPACE, "mvf_input_pipeline: workspace too small");
     MVF_RUN("mvf_input_pipeline", mvf::input_pipeline(frames, prm_f, prm_i, workspace, color_dev, color_aug_dev, B, F, H, W, (cudaStream_t)stream));
+}
+
+static bool dispconv_ok(int B, int C, int H, int W) { return B > 0 && C > 0 && C % 4 == 0 && C <= 64 && H > 0 && W > 0; }
+int mvf_dispconv_fwd(const float* xp, const float* w, const float* bias, float* y, int B, int C, int H, int W, void* stream) {
+    if (!xp || !w || !y || !dispconv_ok(B, C, H, W)) return fail(MVF_ERR_INVALID, "mvf_dispconv_fwd: bad argument (C % 4 == 0, C <= 64)");
+    MVF_RUN("mvf_dispconv_fwd", mvf::dispconv_fwd(xp, w, bias, y, B, C, H, W, (cudaStream_t)stream));
+}
+int mvf_dispconv_dgrad(const float* grad_y, const float* w, float* grad_xp, int B, int C, int H, int W, void* stream) {
+    if (!grad_y || !w || !grad_xp || !dispconv_ok(B, C, H, W)) return fail(MVF_ERR_INVALID, "mvf_dispconv_dgrad: bad argument (C % 4 == 0, C <= 64)");
+    MVF_RUN("mvf_dispconv_dgrad", mvf::dispconv_dgrad(grad_y, w, grad_xp, B, C, H, W, (cudaStream_t)stream));
+}
+size_t mvf_dispconv_wgrad_workspace_floats(long long P, int C) { return (P > 0 && C > 0) ? mvf::dispconv_wgrad_workspace_floats(P, C) : 0; }
+int mvf_dispconv_wgrad(const float* xp, const float* grad_y, float* grad_w, float* grad_b, float* workspace, size_t workspace_floats, int B,
+                       int C, int H, int W, void* stream) {
+    if (!xp || !grad_y || !grad_w || !workspace || !dispconv_ok(B, C, H, W)) return fail(MVF_ERR_INVALID, "mvf_dispconv_wgrad: bad argument (C % 4 == 0, C <= 64)");
+    if (workspace_floats < mvf::dispconv_wgrad_workspace_floats((long long)B * H * W, C)) return fail(MVF_ERR_WORKSPACE, "mvf_dispconv_wgrad: workspace too small");
+    MVF_RUN("mvf_dispconv_wgrad", mvf::dispconv_wgrad(xp, grad_y, grad_w, grad_b, workspace, B, C, H, W, (cudaStream_t)stream));
 }
 
 }  // extern "C"

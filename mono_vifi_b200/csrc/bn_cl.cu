@@ -83,6 +83,36 @@ __global__ void __launch_bounds__(NT) bn_partial_kernel(const float4* __restrict
     }
 }
 
+// Sum of the per-CTA partials of one channel, in a fixed order.  A CTA of 32 x FIN_BL threads owns 32 consecutive channels: thread
+// (cl, bl) adds blocks bl, bl + FIN_BL, ... of channel c0 + cl -- for a given block the 32 channels are one coalesced 128-byte read
+// (round 1 had one warp per channel whose lanes read 32 different cache lines per load: 6-15 us per launch, on the critical path of
+// every BatchNorm) -- and the FIN_BL partial sums meet in shared memory.  Returns true in the thread that holds the result.
+constexpr int FIN_BL = 8;
+__device__ __forceinline__ bool channel_sums(const float* __restrict__ partial, int nblocks, int C, int fold, int& c, double& s, double& ss) {
+    __shared__ double red[FIN_BL][2][32];
+    const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
+    c = blockIdx.x * 32 + cl;
+    const int Cv = fold * C;
+    s = 0.0;
+    ss = 0.0;
+    if (c < C)
+        for (int b = bl; b < nblocks; b += FIN_BL)
+            for (int j = 0; j < fold; ++j) {
+                s += (double)partial[(size_t)b * 2 * Cv + j * C + c];
+                ss += (double)partial[(size_t)b * 2 * Cv + Cv + j * C + c];
+            }
+    red[bl][0][cl] = s;
+    red[bl][1][cl] = ss;
+    __syncthreads();
+    if (bl != 0 || c >= C) return false;
+#pragma unroll
+    for (int q = 1; q < FIN_BL; ++q) {
+        s += red[q][0][cl];
+        ss += red[q][1][cl];
+    }
+    return true;
+}
+
 // forward: mean / biased variance -> (mean, invstd) saved for backward, running statistics updated as nn.BatchNorm2d does.
 // fold > 1 (channel counts with C % 4 == 2, HRNet's 18): the tensor [P][C] is processed as [P / fold][fold * C] so that the float4
 // kernels apply; "virtual" channel j * C + c is real channel c at pixels of parity j.  The partial sums of the fold virtual channels of a
@@ -95,22 +125,9 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int nb
                                        float* __restrict__ beta_v) {
     pdl_sync();
     if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
-    // one warp per channel: lane l adds blocks l, l+32, ...; a fixed shuffle tree combines the lanes
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (c >= C) return;
-    const int Cv = fold * C;
-    double s = 0.0, ss = 0.0;
-    for (int b = lane; b < nblocks; b += 32)
-        for (int j = 0; j < fold; ++j) {
-            s += (double)partial[(size_t)b * 2 * Cv + j * C + c];
-            ss += (double)partial[(size_t)b * 2 * Cv + Cv + j * C + c];
-        }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    }
-    if (lane != 0) return;
+    int c;
+    double s, ss;
+    if (!channel_sums(partial, nblocks, C, fold, c, s, ss)) return;
     const double m = s / (double)P;
     double var = ss / (double)P - m * m;
     if (var < 0.0) var = 0.0;
@@ -135,21 +152,9 @@ __global__ void bn_finalize_bwd_kernel(const float* __restrict__ partial, int nb
                                        float* __restrict__ dbeta, int fold, const float* __restrict__ gamma, float* __restrict__ dgamma_v,
                                        float* __restrict__ dbeta_v, float* __restrict__ gamma_v) {
     pdl_sync();
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (c >= C) return;
-    const int Cv = fold * C;
-    double s = 0.0, ss = 0.0;
-    for (int b = lane; b < nblocks; b += 32)
-        for (int j = 0; j < fold; ++j) {
-            s += (double)partial[(size_t)b * 2 * Cv + j * C + c];
-            ss += (double)partial[(size_t)b * 2 * Cv + Cv + j * C + c];
-        }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    }
-    if (lane != 0) return;
+    int c;
+    double s, ss;
+    if (!channel_sums(partial, nblocks, C, fold, c, s, ss)) return;
     dbeta[c] = (float)s;
     dgamma[c] = (float)ss;
     if (dgamma_v)
@@ -278,20 +283,10 @@ __global__ void bias_finalize_kernel(const float* __restrict__ partial, int nblo
 __global__ void bn_sums_kernel(const float* __restrict__ partial, int nblocks, int C, double count, double* __restrict__ sums,
                                float* __restrict__ local0, float* __restrict__ local1) {
     pdl_sync();
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (c == 0 && lane == 0) sums[2 * C] = count;
-    if (c >= C) return;
-    double s = 0.0, ss = 0.0;
-    for (int b = lane; b < nblocks; b += 32) {
-        s += (double)partial[(size_t)b * 2 * C + c];
-        ss += (double)partial[(size_t)b * 2 * C + C + c];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    }
-    if (lane != 0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) sums[2 * C] = count;
+    int c;
+    double s, ss;
+    if (!channel_sums(partial, nblocks, C, 1, c, s, ss)) return;
     sums[c] = s;
     sums[C + c] = ss;
     if (local0) local0[c] = (float)s;     // backward: d_beta
@@ -398,7 +393,7 @@ cudaError_t bn_forward(const float* x, const float* identity, float* y, const fl
     float* beta_v = fold > 1 ? gamma_v + Cv : nullptr;
     launch_pdl(bn_partial_kernel<false>, dim3((unsigned)(nb)), dim3(NT), (size_t)(2 * rows * C4 * sizeof(float4)), st, (const float4*)x, nullptr, nullptr, nullptr, nullptr,
                                                                             workspace, Pv, C4, 0);
-    launch_pdl(bn_finalize_fwd_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), (size_t)(0), st, (const float*)workspace, nb, C, P, eps, momentum, save_mean, save_invstd,
+    launch_pdl(bn_finalize_fwd_kernel, dim3((unsigned)((C + 31) / 32)), dim3(32 * FIN_BL), (size_t)(0), st, (const float*)workspace, nb, C, P, eps, momentum, save_mean, save_invstd,
                running_mean, running_var, num_batches_tracked, fold, gamma, beta, gamma_v, beta_v);
     const long long total4 = Pv * C4;
     launch_pdl(bn_apply_fwd_kernel, dim3((unsigned)(apply_blocks(total4))), dim3(NT), (size_t)(0), st, (const float4*)x, (const float4*)identity, (float4*)y,
@@ -418,7 +413,7 @@ cudaError_t bn_backward(const float* x, const float* gy, const float* y, const f
     float* gamma_v = fold > 1 ? dbeta_v + Cv : nullptr;
     launch_pdl(bn_partial_kernel<true>, dim3((unsigned)(nb)), dim3(NT), (size_t)(2 * rows * C4 * sizeof(float4)), st, (const float4*)x, (const float4*)gy, (const float4*)y,
                                                                            save_mean, save_invstd, workspace, Pv, C4, relu);
-    launch_pdl(bn_finalize_bwd_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), (size_t)(0), st, (const float*)workspace, nb, C, dgamma, dbeta, fold, gamma, dgamma_v,
+    launch_pdl(bn_finalize_bwd_kernel, dim3((unsigned)((C + 31) / 32)), dim3(32 * FIN_BL), (size_t)(0), st, (const float*)workspace, nb, C, dgamma, dbeta, fold, gamma, dgamma_v,
                dbeta_v, gamma_v);
     const long long total4 = Pv * C4;
     launch_pdl(bn_apply_bwd_kernel, dim3((unsigned)(apply_blocks(total4))), dim3(NT), (size_t)(0), st, (const float4*)x, (const float4*)gy, (const float4*)y, (float4*)gx,
@@ -433,7 +428,7 @@ cudaError_t bn_sync_stats_fwd(const float* x, double* sums, float* workspace, lo
     const int rows = NT / C4 > 0 ? NT / C4 : 1;
     launch_pdl(bn_partial_kernel<false>, dim3((unsigned)nb), dim3(NT), (size_t)(2 * rows * C4 * sizeof(float4)), st, (const float4*)x,
                nullptr, nullptr, nullptr, nullptr, workspace, P, C4, 0);
-    launch_pdl(bn_sums_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), (size_t)0, st, (const float*)workspace, nb, C, (double)P, sums,
+    launch_pdl(bn_sums_kernel, dim3((unsigned)((C + 31) / 32)), dim3(32 * FIN_BL), (size_t)0, st, (const float*)workspace, nb, C, (double)P, sums,
                nullptr, nullptr);
     return cudaGetLastError();
 }
@@ -458,7 +453,7 @@ cudaError_t bn_sync_stats_bwd(const float* x, const float* gy, const float* y, c
     const int rows = NT / C4 > 0 ? NT / C4 : 1;
     launch_pdl(bn_partial_kernel<true>, dim3((unsigned)nb), dim3(NT), (size_t)(2 * rows * C4 * sizeof(float4)), st, (const float4*)x,
                (const float4*)gy, (const float4*)y, save_mean, save_invstd, workspace, P, C4, relu);
-    launch_pdl(bn_sums_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), (size_t)0, st, (const float*)workspace, nb, C, (double)P, sums,
+    launch_pdl(bn_sums_kernel, dim3((unsigned)((C + 31) / 32)), dim3(32 * FIN_BL), (size_t)0, st, (const float*)workspace, nb, C, (double)P, sums,
                dbeta, dgamma);
     return cudaGetLastError();
 }

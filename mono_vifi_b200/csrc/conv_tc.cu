@@ -19,6 +19,7 @@
 #include "conv_tc.cuh"
 
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "pdl.cuh"
@@ -33,6 +34,7 @@ constexpr int TILE_M = 128;                         // output pixels per CTA (= 
 constexpr int BLOCK_K = 32, KGROUPS = BLOCK_K / 8;  // channels per pipeline stage, UMMA K = 8 (tf32)
 constexpr int A_STAGE_BYTES = TILE_M * BLOCK_K * 4; // 16 KB
 constexpr int NTHREADS = 192;
+constexpr int PATCH_THREADS = 224;  // conv_patch_kernel: warp 6 is the second MMA issuer (stacked tile mt = 1)
 
 template <int N_TILE>
 struct Cfg {
@@ -446,7 +448,7 @@ struct PatchArgs {
 // tile boundaries (patch double buffer + NB-deep filter ring), the MMA issuer alternates between two accumulator
 // buffers in TMEM, and the four epilogue warps drain one buffer while the next tile is being multiplied.
 template <int N_TILE, int MT, int NB>
-__global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(PATCH_THREADS, 1) conv_patch_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                  const __grid_constant__ CUtensorMap mapB,
                                                                  const __grid_constant__ CUtensorMap mapY, const PatchArgs p) {
     constexpr int B_STAGE_BYTES = N_TILE * BLOCK_K * 4;
@@ -475,13 +477,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&a_full[s], 1);
-            mbar_init(&a_empty[s], 1);
-            mbar_init(&acc_full[s], 1);
+            mbar_init(&a_empty[s], MT);     // one commit per MMA issuer (one issuer warp per stacked tile)
+            mbar_init(&acc_full[s], MT);
             mbar_init(&acc_empty[s], 128);  // every epilogue thread arrives
         }
         for (int s = 0; s < NB; ++s) {
             mbar_init(&b_full[s], 1);
-            mbar_init(&b_empty[s], 1);
+            mbar_init(&b_empty[s], MT);
         }
         fence_barrier_init();
     }
@@ -535,53 +537,91 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_patch_kernel(const __grid_co
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues =====
-        constexpr uint32_t idesc = make_idesc_tf32(TILE_M, N_TILE, 0, 0);
-        const uint64_t desc_hi = make_smem_desc(0, 16, 1024, SWZ_128B);  // everything but the start address
-        const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
-        int bs = 0, bph = 0, ab = 0, aph = 0, acc = 0, accph = 0;
-        if (p.b_resident) mbar_wait(&b_full[0], 0);
-        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-            mbar_wait(&acc_empty[acc], accph ^ 1);  // the epilogue has drained this accumulator buffer
-            tc_fence_after();
-            const uint32_t d_base = tmem_d + (uint32_t)(acc * ACC_COLS);
-            for (int cb = 0; cb < p.n_cblk; ++cb) {
-                mbar_wait(&a_full[ab], aph);
-                const uint32_t a_base = smA_u + (uint32_t)(ab * p.patch_stride);
-                int kh = 0, kw = 0;
-                const int ng = (cb == p.n_cblk - 1) ? p.kg_last : KGROUPS;  // all-zero channel groups are not multiplied
-                for (int tp = 0; tp < taps; ++tp) {
-                    if (!p.b_resident) mbar_wait(&b_full[bs], bph);
-                    tc_fence_after();
-                    // lo word = start address (14 bits) below the LBO field: advancing is a plain 32-bit add
-                    const uint32_t b_lo = ((smB_u + (uint32_t)((p.b_resident ? tp * p.n_cblk + cb : bs) * B_STAGE_BYTES)) >> 4) | (uint32_t)desc_hi;
-                    const uint64_t d_up = desc_hi & 0xFFFFFFFF00000000ull;
-                    if (elect_one()) {
-#pragma unroll
-                        for (int mt = 0; mt < MT; ++mt) {
-                            if (p.dbg & 4) break;
-                            const uint32_t a_lo = ((a_base + (uint32_t)((mt * p.TR + kh) * p.P + kw) * 128u) >> 4) | (uint32_t)desc_hi;
-#pragma unroll
-                            for (int kg = 0; kg < KGROUPS; ++kg)
-                                if (kg < ng)
-                                    umma_tf32(d_base + (uint32_t)(mt * N_TILE), d_up | (uint64_t)(a_lo + 2 * kg),
-                                              d_up | (uint64_t)(b_lo + 2 * kg), idesc, (cb > 0 || tp > 0 || kg > 0) ? 1u : 0u);
-                        }
-                        if (!p.b_resident) umma_commit(&b_empty[bs]);
-                    }
-                    __syncwarp();
-                    if (++bs == p.nb) { bs = 0; bph ^= 1; }
-                    if (++kw == p.KW) { kw = 0; ++kh; }
-                }
-                if (elect_one()) umma_commit(&a_empty[ab]);
-                __syncwarp();
-                if (++ab == 2) { ab = 0; aph ^= 1; }
+    } else if (warp == 1 || warp == 6) {
+        // ===== MMA issuers: warp 1 owns the stacked tile mt = 0, warp 6 the tile mt = 1; ONE lane of each runs the whole loop =====
+        // Measured (tools/conv_sweep.py, MVF_CONV_DBG=8: no TMA loads at all): every layer shape ran exactly as long without its
+        // loads as with them, and ncu put the tensor pipe at 40 % of the active cycles with the operand fetch at its ideal 64
+        // wavefronts per MMA -- the kernel is bound by the ISSUE of the MMAs: one thread sustains one tcgen05.mma per 60-80 cycles
+        // (N = 64: 32 cycles of tensor work, N = 128: 64) plus ~220 cycles of barrier / descriptor bookkeeping per tap.  So the
+        // issue work is (a) thinned -- descriptor words advance by adds, the accumulate flag is a register that flips once per
+        // tile, full 32-channel blocks take an unpredicated path, no ELECT / VOTE / BRA.DIV per tap -- and (b) split: each stacked
+        // tile has its own accumulator columns and its own issuing warp, so two instruction streams feed the tensor pipe and the
+        // order of the additions into any one accumulator stays fixed (results are bitwise repeatable).  The barriers the
+        // issuers release (a_empty, b_empty, acc_full) count MT arrivals.
+        const int my_mt = (warp == 1) ? 0 : 1;
+        if (my_mt >= MT) {
+            // no second stacked tile: warp 6 has nothing to do
+        } else
+        if (elect_one()) {   // (elect.sync rather than lane == 0: the compiler then knows a single lane is active and moves the operands to
+                             //  uniform registers with one R2UR each instead of a per-MMA ELECT / R2UR.BROADCAST loop)
+            constexpr uint32_t idesc = make_idesc_tf32(TILE_M, N_TILE, 0, 0);
+            const uint64_t desc_hi = make_smem_desc(0, 16, 1024, SWZ_128B);  // everything but the start address
+            const uint64_t d_up = desc_hi & 0xFFFFFFFF00000000ull;
+            const uint32_t lo_const = (uint32_t)desc_hi;                     // LBO field; the start address (>> 4) is OR-ed / added below
+            const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
+            const uint32_t mt_step = (uint32_t)(p.TR * p.P) * 8u;            // 16-byte units between the stacked tiles' first rows
+            const uint32_t row_step = (uint32_t)(p.P - p.KW) * 8u;           // extra advance at the end of a filter row
+            constexpr uint32_t B_UNITS = B_STAGE_BYTES >> 4;
+            const uint32_t b_ring0 = (smB_u >> 4) | lo_const;
+            const int resident = p.b_resident;
+            int bs = 0, bph = 0, ab = 0, aph = 0, acc = 0, accph = 0;
+            uint32_t b_ring = b_ring0;
+            if (resident) {
+                mbar_wait(&b_full[0], 0);
+                tc_fence_after();
             }
-            if (elect_one()) umma_commit(&acc_full[acc]);
-            __syncwarp();
-            if (++acc == 2) { acc = 0; accph ^= 1; }
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+                mbar_wait(&acc_empty[acc], accph ^ 1);  // the epilogue has drained this accumulator buffer
+                tc_fence_after();
+                const uint32_t d_base = tmem_d + (uint32_t)(acc * ACC_COLS + my_mt * N_TILE);
+                uint32_t accum = 0;
+                for (int cb = 0; cb < p.n_cblk; ++cb) {
+                    mbar_wait(&a_full[ab], aph);
+                    tc_fence_after();
+                    uint32_t a_tap = (((smA_u + (uint32_t)(ab * p.patch_stride)) >> 4) | lo_const) + (uint32_t)my_mt * mt_step;
+                    uint32_t b_res = b_ring0 + (uint32_t)cb * B_UNITS;        // resident bank: tile (tap, cb) at (tap * n_cblk + cb)
+                    const uint32_t b_res_step = (uint32_t)p.n_cblk * B_UNITS;
+                    const int ng = (cb == p.n_cblk - 1) ? p.kg_last : KGROUPS;  // all-zero channel groups are not multiplied
+                    int kw = 0;
+                    for (int tp = 0; tp < taps; ++tp) {
+                        uint32_t b_lo;
+                        if (resident) {
+                            b_lo = b_res;
+                            b_res += b_res_step;
+                        } else {
+                            mbar_wait(&b_full[bs], bph);
+                            tc_fence_after();
+                            b_lo = b_ring;
+                        }
+                        if (!(p.dbg & 4)) {
+                            umma_tf32(d_base, d_up | (uint64_t)a_tap, d_up | (uint64_t)b_lo, idesc, accum);
+                            if (ng == KGROUPS) {
+#pragma unroll
+                                for (int kg = 1; kg < KGROUPS; ++kg)
+                                    umma_tf32_acc(d_base, d_up | (uint64_t)(a_tap + 2 * kg), d_up | (uint64_t)(b_lo + 2 * kg), idesc);
+                            } else {
+#pragma unroll
+                                for (int kg = 1; kg < KGROUPS; ++kg)
+                                    if (kg < ng) umma_tf32_acc(d_base, d_up | (uint64_t)(a_tap + 2 * kg), d_up | (uint64_t)(b_lo + 2 * kg), idesc);
+                            }
+                        }
+                        accum = 1;
+                        if (!resident) {
+                            umma_commit(&b_empty[bs]);
+                            b_ring += B_UNITS;
+                            if (++bs == p.nb) { bs = 0; bph ^= 1; b_ring = b_ring0; }
+                        }
+                        a_tap += 8;
+                        if (++kw == p.KW) { kw = 0; a_tap += row_step; }
+                    }
+                    umma_commit(&a_empty[ab]);
+                    if (++ab == 2) { ab = 0; aph ^= 1; }
+                }
+                umma_commit(&acc_full[acc]);
+                if (++acc == 2) { acc = 0; accph ^= 1; }
+            }
         }
+        __syncwarp();
     } else {
         // ===== epilogue: warps 2..5 own the TMEM lane quarter (warp % 4); one thread = one patch position =====
         // TMEM -> registers -> bias / activation -> swizzled shared-memory slab [128 positions][SLAB channels] -> one TMA
@@ -788,7 +828,7 @@ cudaError_t launch_patch(const CUtensorMap& mapA, const CUtensorMap& mapB, const
         if (n_sm <= 0) n_sm = 148;
     }
     const int grid = a.n_tiles < n_sm ? a.n_tiles : n_sm;
-    return launch_pdl(conv_patch_kernel<N_TILE, MT, NB>, dim3(grid), dim3(NTHREADS), (size_t)smem, st, mapA, mapB, mapY, a);
+    return launch_pdl(conv_patch_kernel<N_TILE, MT, NB>, dim3(grid), dim3(PATCH_THREADS), (size_t)smem, st, mapA, mapB, mapY, a);
 }
 
 }  // namespace
@@ -829,9 +869,6 @@ void set_debug_buffer(float* p) { g_dbg = p; }
 
 static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const float* w_packed, const float* bias, float* y,
                                       int act, cudaStream_t st, const char** why, EncodeTiledFn enc, int Ho, int Wo, const float* slope) {
-    int n_tile = 16;
-    while (n_tile < d.Cout && n_tile < 128) n_tile *= 2;
-    const int n_ntiles = (d.Cout + n_tile - 1) / n_tile;
     // column segmentation: the split of an output row into nseg pieces that needs the fewest 128-position tiles
     int best_nseg = 1;
     long long best_tiles = -1;
@@ -857,12 +894,71 @@ static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const f
     a.PWo = (Wo + best_nseg - 1) / best_nseg;
     a.P = a.PWo + d.KW - 1;
     a.TR = TILE_M / a.P;
-    // two stacked tiles per CTA (shared patch and filter tiles) when that still leaves about two waves of CTAs
-    int MT = 1;
+    // Tile shape (N_TILE output channels x MT stacked 128-position tiles per CTA) from a cost model.  Measured on B200
+    // (profiles/r2_conv_layers_cfg2.txt): the C >= 64 layers run at the L2 -> SM bandwidth of the bytes their tiles pull in -- every
+    // tile re-reads its (taps x Cin x N_TILE) filter slice, 4-8x the patch bytes -- about 5 TB/s aggregate, not at the MMA rate:
+    //   64->64 @48x160: 114 MB / 30.6 us, 128->128 @24x80: 146 MB / 31.3 us, 256->256 @12x40: 140 MB / 31.1 us, 512->512 @6x20: 263 MB / 51.3 us.
+    // The model charges a candidate max(bytes / L2 rate, waves x max(MMA cycles, per-SM ingest cycles)) and takes the cheapest; the
+    // round-1 rule (widest N <= 128, MT = 2 only with >= 2 waves of CTAs) remains as MVF_CONV_TILE_RULE=r1 for A/B timing.
+    int n_tile = 16, MT = 1;
     {
-        const long long ctas2 = (long long)d.B * best_nseg * ((Ho + 2 * a.TR - 1) / (2 * a.TR)) * n_ntiles;
-        if (ctas2 >= 2 * 148 && Ho >= 2 * a.TR && !getenv("MVF_CONV_MT1")) MT = 2;
+        int n_wide = 16;
+        while (n_wide < d.Cout && n_wide < 128) n_wide *= 2;
+        const int taps = d.KH * d.KW, n_cblk = (d.Cin + BLOCK_K - 1) / BLOCK_K;
+        const char* rule = getenv("MVF_CONV_TILE_RULE");
+        if (rule && rule[0] == 'r') {
+            n_tile = n_wide;
+            const long long ctas2 = (long long)d.B * best_nseg * ((Ho + 2 * a.TR - 1) / (2 * a.TR)) * ((d.Cout + n_tile - 1) / n_tile);
+            if (ctas2 >= 2 * 148 && Ho >= 2 * a.TR) MT = 2;
+        } else if (rule) {  // "N,MT": forced shape (tools/conv_layers.py sweeps)
+            n_tile = atoi(rule);
+            const char* c = strchr(rule, ',');
+            MT = c ? atoi(c + 1) : 1;
+            if ((n_tile != 16 && n_tile != 32 && n_tile != 64 && n_tile != 128) || (MT != 1 && MT != 2)) {
+                *why = "MVF_CONV_TILE_RULE: N in {16,32,64,128}, MT in {1,2}";
+                return cudaErrorInvalidValue;
+            }
+        } else {
+            double best_cost = -1.0;
+            for (int nt = 16; nt <= n_wide; nt *= 2)
+                for (int mt = 1; mt <= 2; ++mt) {
+                    if (mt == 2 && Ho < 2 * a.TR) continue;
+                    const long long R = mt * a.TR + d.KH - 1;
+                    const long long patch = R * a.P * BLOCK_K * 4;
+                    const long long pstride = ((patch + (d.KW - 1 + TILE_M - a.TR * a.P) * 128) + 1023) / 1024 * 1024;
+                    const int slab = nt < 32 ? nt : 32;
+                    long long ring = (227 * 1024 - 1280 - 2 * TILE_M * slab * 4 - 2 * pstride) / (nt * BLOCK_K * 4);
+                    if (ring < 2) continue;
+                    if (ring > (nt >= 128 ? 8 : 16)) ring = nt >= 128 ? 8 : 16;
+                    const long long n_nt = (d.Cout + nt - 1) / nt;
+                    const long long tiles = (long long)d.B * best_nseg * ((Ho + mt * a.TR - 1) / (mt * a.TR)) * n_nt;
+                    const long long ctas = tiles < 148 ? tiles : 148;
+                    const long long per_cta = (tiles + ctas - 1) / ctas;
+                    const bool resident = n_nt == 1 && taps * n_cblk <= ring;
+                    const double filt = (double)taps * n_cblk * nt * BLOCK_K * 4;
+                    const double a_bytes = (double)n_cblk * patch, o_bytes = (double)mt * TILE_M * nt * 4;
+                    const double l2_bytes = tiles * (a_bytes + o_bytes + (resident ? 0.0 : filt)) + (resident ? ctas * filt : 0.0);
+                    // per tap: each issuer warp (one per stacked tile) spends ~220 cycles of bookkeeping + ~75 per MMA; the tensor pipe
+                    // needs nt / 2 cycles per MMA of all stacked tiles
+                    const double issue_tap = 220.0 + KGROUPS * (nt / 2 > 75 ? nt / 2 : 75.0), exec_tap = (double)mt * KGROUPS * (nt / 2);
+                    const double mma_clk = (double)taps * n_cblk * (issue_tap > exec_tap ? issue_tap : exec_tap);
+                    const double ingest_clk = (a_bytes + (resident ? 0.0 : filt)) / 48.0;
+                    const double sm_clk = per_cta * (mma_clk > ingest_clk ? mma_clk : ingest_clk) + 3000.0 * per_cta + 4000.0;
+                    const double l2_clk = l2_bytes / 2500.0;
+                    const double cost = sm_clk > l2_clk ? sm_clk : l2_clk;
+                    if (best_cost < 0.0 || cost < best_cost) {
+                        best_cost = cost;
+                        n_tile = nt;
+                        MT = mt;
+                    }
+                }
+            if (best_cost < 0.0) {
+                *why = "patch does not fit in shared memory";
+                return cudaErrorInvalidValue;
+            }
+        }
     }
+    const int n_ntiles = (d.Cout + n_tile - 1) / n_tile;
     a.R = MT * a.TR + d.KH - 1;
     a.tiles_y = (Ho + MT * a.TR - 1) / (MT * a.TR);
     a.n_cblk = (d.Cin + BLOCK_K - 1) / BLOCK_K;

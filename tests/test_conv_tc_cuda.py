@@ -228,3 +228,34 @@ def test_dgrad_stride2_vs_fp64(case):
     ref = xr.grad.float()
     err = (gx - ref).abs().max().item()
     assert err <= 3e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16, 64), (1, 64, 9, 33), (3, 32, 7, 5), (12, 16, 192, 640)])
+def test_dispconv_direct_kernels_vs_fp64(case):
+    """Conv3x3(C, 1) on a padded channels-last feature (csrc/dispconv.cu): fp32 FMA chains, so 1e-5 of the magnitude; the weight
+    gradient's split reduction has a fixed order (bitwise repeatable)."""
+    import torch
+    from mono_vifi_b200 import conv_tc
+    B, C, H, W = case
+    g = torch.Generator(device="cuda").manual_seed(11)
+    xp = torch.randn(B, C, H + 2, W + 2, device="cuda", generator=g).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = (torch.randn(1, C, 3, 3, device="cuda", generator=g) / (C * 9) ** 0.5).requires_grad_(True)
+    b = torch.randn(1, device="cuda", generator=g, requires_grad=True)
+    assert conv_tc.dispconv_supported(xp, w, 1, 0)
+    n0 = dict(conv_tc.launches)
+    y = conv_tc.conv2d(xp, w, b, 1, 0)
+    gy = torch.randn(y.shape, device="cuda", generator=g)
+    y.backward(gy)
+    assert conv_tc.launches["fprop"] == n0["fprop"] + 1
+    xr, wr, br = (t.detach().double().requires_grad_(True) for t in (xp, w, b))
+    yr = torch.nn.functional.conv2d(xr, wr, br)
+    yr.backward(gy.double())
+    for got, ref in ((y, yr), (xp.grad, xr.grad), (w.grad, wr.grad), (b.grad, br.grad)):
+        ref = ref.float()
+        assert got.shape == ref.shape
+        assert (got - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-6, (got - ref).abs().max().item()
+    gw1 = w.grad.clone()
+    w.grad = None
+    xp.grad = None
+    conv_tc.conv2d(xp, w, b, 1, 0).backward(gy)
+    assert torch.equal(gw1, w.grad)
