@@ -34,13 +34,14 @@ constexpr int TILE_M = 128;                         // output pixels per CTA (= 
 constexpr int BLOCK_K = 32, KGROUPS = BLOCK_K / 8;  // channels per pipeline stage, UMMA K = 8 (tf32)
 constexpr int A_STAGE_BYTES = TILE_M * BLOCK_K * 4; // 16 KB
 constexpr int NTHREADS = 192;
+constexpr int IGEMM_THREADS = 224;  // conv_igemm_kernel: warp 6 is the second MMA issuer (odd pipeline iterations)
 constexpr int PATCH_THREADS = 224;  // conv_patch_kernel: warp 6 is the second MMA issuer (stacked tile mt = 1)
 
 template <int N_TILE>
 struct Cfg {
     static constexpr int B_STAGE_BYTES = N_TILE * BLOCK_K * 4;
     static constexpr int STAGES = (N_TILE >= 256) ? 4 : ((N_TILE >= 128) ? 3 : 4);
-    static constexpr int TMEM_COLS = N_TILE < 32 ? 32 : N_TILE;
+    static constexpr int TMEM_COLS = (2 * N_TILE) < 32 ? 32 : (2 * N_TILE);  // conv_igemm_kernel: one accumulator per MMA issuer
     static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
@@ -100,7 +101,7 @@ __device__ __forceinline__ void bias_act(float (&v)[CH], const float* __restrict
 }
 
 template <int N_TILE>
-__global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(IGEMM_THREADS) conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA,
                                                               const __grid_constant__ CUtensorMap mapB, const ConvArgs p) {
     using C = Cfg<N_TILE>;
     extern __shared__ unsigned char smem_raw[];
@@ -119,15 +120,18 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
     const int TW = 1 << p.tw_log2, TH = TILE_M >> p.tw_log2;
     const int x0 = tx * TW, y0 = ty * TH, n0 = blockIdx.y * N_TILE;
     const int n_iters = p.KH * p.KW * p.n_cblk;
+    // two MMA issuers (see conv_patch_kernel): warp 1 multiplies the even pipeline iterations into accumulator columns [0, N), warp 6
+    // the odd ones into [N, 2N); the epilogue adds the two halves (a fixed order, so results stay bitwise repeatable)
+    const int n_issuers = n_iters >= 2 ? 2 : 1;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], n_issuers);   // the owner's commit + the other issuer's "I have seen this phase"
         }
-        mbar_init(tmem_full_bar, 1);
+        mbar_init(tmem_full_bar, n_issuers);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -157,27 +161,43 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
                 tma_load_3d(smB + s * C::B_STAGE_BYTES, &mapB, &full_bar[s], 0, n0, it);
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+    } else if (warp == 1 || warp == 6) {
+        // ===== MMA issuers =====
+        const int issuer = warp == 1 ? 0 : 1;
+        if (issuer < n_issuers && elect_one()) {
             constexpr uint32_t idesc = make_idesc_tf32(TILE_M, N_TILE, /*A K-major*/ 0, /*B K-major*/ 0);
+            // K-major SW128: rows of 32 k (128 B), 8-row groups 1024 B apart (SBO); k-group kg starts 32 B (2 units) in
+            const uint64_t desc_hi = make_smem_desc(0, 16, 1024, SWZ_128B);
+            const uint64_t d_up = desc_hi & 0xFFFFFFFF00000000ull;
+            const uint32_t lo_const = (uint32_t)desc_hi;
+            const uint32_t a0 = (smem_u32(smA) >> 4) | lo_const, b0 = (smem_u32(smB) >> 4) | lo_const;
+            const uint32_t d = tmem_d + (uint32_t)(issuer * N_TILE);
+            int s = 0;
+            uint32_t ph = 0, accum = 0;
+            uint32_t a_lo = a0, b_lo = b0;
+            // Both issuers wait on EVERY stage barrier, in order, and both release the stage (the owner of the iteration with the
+            // commit of its MMAs, the other with a plain arrive): try_wait.parity only tells the current phase from the preceding
+            // one, so an issuer must never fall a whole ring generation behind the barriers it polls.
             for (int it = 0; it < n_iters; ++it) {
-                const int s = it % C::STAGES;
-                const uint32_t ph = (it / C::STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
-                tc_fence_after();
-                const uint32_t a_base = smem_u32(smA + s * A_STAGE_BYTES), b_base = smem_u32(smB + s * C::B_STAGE_BYTES);
+                if ((it & 1) != issuer && n_issuers == 2) {
+                    mbar_arrive(&empty_bar[s]);
+                } else {
+                    tc_fence_after();
+                    umma_tf32(d, d_up | (uint64_t)a_lo, d_up | (uint64_t)b_lo, idesc, accum);
 #pragma unroll
-                for (int kg = 0; kg < KGROUPS; ++kg) {
-                    // K-major SW128: rows of 32 k (128 B), 8-row groups 1024 B apart (SBO); k-group kg starts 32 B in
-                    const uint64_t adesc = make_smem_desc(a_base + kg * 32, 16, 1024, SWZ_128B);
-                    const uint64_t bdesc = make_smem_desc(b_base + kg * 32, 16, 1024, SWZ_128B);
-                    umma_tf32(tmem_d, adesc, bdesc, idesc, (it > 0 || kg > 0) ? 1u : 0u);
+                    for (int kg = 1; kg < KGROUPS; ++kg)
+                        umma_tf32_acc(d, d_up | (uint64_t)(a_lo + 2 * kg), d_up | (uint64_t)(b_lo + 2 * kg), idesc);
+                    accum = 1;
+                    umma_commit(&empty_bar[s]);  // frees the stage when these MMAs have read it
                 }
-                umma_commit(&empty_bar[s]);  // frees the stage when these MMAs have read it
+                a_lo += A_STAGE_BYTES >> 4;
+                b_lo += C::B_STAGE_BYTES >> 4;
+                if (++s == C::STAGES) { s = 0; ph ^= 1; a_lo = a0; b_lo = b0; }
             }
             umma_commit(tmem_full_bar);
         }
+        __syncwarp();
     } else {
         // ===== epilogue: warps 2..5 own the TMEM lane quarter (warp % 4); one thread = one output pixel =====
         const int q = warp & 3;
@@ -196,10 +216,17 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
             if constexpr (CH == 32) tmem_ld32(taddr, r);
             else tmem_ld16(taddr, r);
             tmem_ld_wait();
-            if (!pix_ok) continue;
             float v[CH];
 #pragma unroll
             for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+            if (n_issuers == 2) {   // (uniform) the odd iterations' accumulator
+                if constexpr (CH == 32) tmem_ld32(taddr + (uint32_t)N_TILE, r);
+                else tmem_ld16(taddr + (uint32_t)N_TILE, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < CH; ++j) v[j] += __uint_as_float(r[j]);
+            }
+            if (!pix_ok) continue;
             bias_act<CH>(v, p.bias, n0 + c0, p.Cout, p.act, p.slope);
             if (vec_ok) {
 #pragma unroll
@@ -217,9 +244,9 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
     __syncthreads();
     if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
         const float* src = reinterpret_cast<const float*>(smA);
-        for (int i = threadIdx.x; i < A_STAGE_BYTES / 4; i += NTHREADS) p.dbg[i] = src[i];
+        for (int i = threadIdx.x; i < A_STAGE_BYTES / 4; i += IGEMM_THREADS) p.dbg[i] = src[i];
         src = reinterpret_cast<const float*>(smB);
-        for (int i = threadIdx.x; i < C::B_STAGE_BYTES / 4; i += NTHREADS) p.dbg[A_STAGE_BYTES / 4 + i] = src[i];
+        for (int i = threadIdx.x; i < C::B_STAGE_BYTES / 4; i += IGEMM_THREADS) p.dbg[A_STAGE_BYTES / 4 + i] = src[i];
         if (threadIdx.x == 0) p.dbg[A_STAGE_BYTES / 4 + C::B_STAGE_BYTES / 4] = __uint_as_float(tmem_d);
     }
     if (warp == 1) {
@@ -452,7 +479,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, 1) conv_patch_kernel(const __gr
                                                                  const __grid_constant__ CUtensorMap mapB,
                                                                  const __grid_constant__ CUtensorMap mapY, const PatchArgs p) {
     constexpr int B_STAGE_BYTES = N_TILE * BLOCK_K * 4;
-    constexpr int ACC_COLS = MT * N_TILE;  // one accumulator buffer
+    constexpr int ACC_COLS = 2 * N_TILE;   // one accumulator buffer: MT = 2: the two stacked tiles; MT = 1: the even / odd taps' partial sums
     constexpr int TMEM_COLS = (2 * ACC_COLS) < 32 ? 32 : (2 * ACC_COLS);
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -477,13 +504,13 @@ __global__ void __launch_bounds__(PATCH_THREADS, 1) conv_patch_kernel(const __gr
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&a_full[s], 1);
-            mbar_init(&a_empty[s], MT);     // one commit per MMA issuer (one issuer warp per stacked tile)
-            mbar_init(&acc_full[s], MT);
+            mbar_init(&a_empty[s], 2);      // one commit per MMA issuer
+            mbar_init(&acc_full[s], 2);
             mbar_init(&acc_empty[s], 128);  // every epilogue thread arrives
         }
         for (int s = 0; s < NB; ++s) {
             mbar_init(&b_full[s], 1);
-            mbar_init(&b_empty[s], MT);
+            mbar_init(&b_empty[s], 2);      // both issuers release a filter tile (MT = 1: the one whose tap it is not, right after seeing it)
         }
         fence_barrier_init();
     }
@@ -548,10 +575,10 @@ __global__ void __launch_bounds__(PATCH_THREADS, 1) conv_patch_kernel(const __gr
         // tile has its own accumulator columns and its own issuing warp, so two instruction streams feed the tensor pipe and the
         // order of the additions into any one accumulator stays fixed (results are bitwise repeatable).  The barriers the
         // issuers release (a_empty, b_empty, acc_full) count MT arrivals.
+        // With a single tile per CTA (MT = 1) the two issuers take alternate taps (counted across channel blocks) into two partial
+        // accumulators that the epilogue adds.
         const int my_mt = (warp == 1) ? 0 : 1;
-        if (my_mt >= MT) {
-            // no second stacked tile: warp 6 has nothing to do
-        } else
+        constexpr bool SPLIT_TAPS = (MT == 1);
         if (elect_one()) {   // (elect.sync rather than lane == 0: the compiler then knows a single lane is active and moves the operands to
                              //  uniform registers with one R2UR each instead of a per-MMA ELECT / R2UR.BROADCAST loop)
             constexpr uint32_t idesc = make_idesc_tf32(TILE_M, N_TILE, 0, 0);
@@ -559,7 +586,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, 1) conv_patch_kernel(const __gr
             const uint64_t d_up = desc_hi & 0xFFFFFFFF00000000ull;
             const uint32_t lo_const = (uint32_t)desc_hi;                     // LBO field; the start address (>> 4) is OR-ed / added below
             const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
-            const uint32_t mt_step = (uint32_t)(p.TR * p.P) * 8u;            // 16-byte units between the stacked tiles' first rows
+            const uint32_t mt_step = SPLIT_TAPS ? 0u : (uint32_t)(p.TR * p.P) * 8u;  // 16-byte units between the stacked tiles' first rows
             const uint32_t row_step = (uint32_t)(p.P - p.KW) * 8u;           // extra advance at the end of a filter row
             constexpr uint32_t B_UNITS = B_STAGE_BYTES >> 4;
             const uint32_t b_ring0 = (smB_u >> 4) | lo_const;
@@ -575,6 +602,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, 1) conv_patch_kernel(const __gr
                 tc_fence_after();
                 const uint32_t d_base = tmem_d + (uint32_t)(acc * ACC_COLS + my_mt * N_TILE);
                 uint32_t accum = 0;
+                int par = 0;                            // parity of the tap counter within the tile
                 for (int cb = 0; cb < p.n_cblk; ++cb) {
                     mbar_wait(&a_full[ab], aph);
                     tc_fence_after();
@@ -584,16 +612,20 @@ __global__ void __launch_bounds__(PATCH_THREADS, 1) conv_patch_kernel(const __gr
                     const int ng = (cb == p.n_cblk - 1) ? p.kg_last : KGROUPS;  // all-zero channel groups are not multiplied
                     int kw = 0;
                     for (int tp = 0; tp < taps; ++tp) {
+                        const bool mine = !SPLIT_TAPS || par == my_mt;
+                        par ^= 1;
                         uint32_t b_lo;
                         if (resident) {
                             b_lo = b_res;
                             b_res += b_res_step;
                         } else {
+                            // both issuers wait on EVERY filter-tile barrier, in order (a thread that skipped a phase of a barrier
+                            // could later find it one phase behind and take that for "complete": TMA completions are not ordered)
                             mbar_wait(&b_full[bs], bph);
-                            tc_fence_after();
+                            if (mine) tc_fence_after();
                             b_lo = b_ring;
                         }
-                        if (!(p.dbg & 4)) {
+                        if (mine && !(p.dbg & 4)) {
                             umma_tf32(d_base, d_up | (uint64_t)a_tap, d_up | (uint64_t)b_lo, idesc, accum);
                             if (ng == KGROUPS) {
 #pragma unroll
@@ -605,9 +637,12 @@ __global__ void __launch_bounds__(PATCH_THREADS, 1) conv_patch_kernel(const __gr
                                     if (kg < ng) umma_tf32_acc(d_base, d_up | (uint64_t)(a_tap + 2 * kg), d_up | (uint64_t)(b_lo + 2 * kg), idesc);
                             }
                         }
-                        accum = 1;
+                        if (mine) accum = 1;
                         if (!resident) {
-                            umma_commit(&b_empty[bs]);
+                            // (MT = 1) the other issuer only reports that it has seen this phase: try_wait.parity tells the current
+                            // phase from the preceding one only, so no issuer may fall a ring generation behind
+                            if (mine) umma_commit(&b_empty[bs]);
+                            else mbar_arrive(&b_empty[bs]);
                             b_ring += B_UNITS;
                             if (++bs == p.nb) { bs = 0; bph ^= 1; b_ring = b_ring0; }
                         }
@@ -655,6 +690,13 @@ __global__ void __launch_bounds__(PATCH_THREADS, 1) conv_patch_kernel(const __gr
                     float v[SLAB];
 #pragma unroll
                     for (int jj = 0; jj < SLAB; ++jj) v[jj] = __uint_as_float(rr[jj]);
+                    if constexpr (MT == 1) {          // the odd taps' partial sums
+                        if constexpr (SLAB == 32) tmem_ld32(taddr + (uint32_t)N_TILE, rr);
+                        else tmem_ld16(taddr + (uint32_t)N_TILE, rr);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int jj = 0; jj < SLAB; ++jj) v[jj] += __uint_as_float(rr[jj]);
+                    }
                     bias_act<SLAB>(v, p.bias, n0 + c0, p.Cout, p.act, p.slope);
                     if (use_tma) {
                         // the staging buffer must have been read by the TMA store issued two slabs ago
@@ -806,7 +848,7 @@ cudaError_t launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const ConvA
         attr_set = true;
     }
     dim3 grid(B * a.tiles_x * a.tiles_y, (a.Cout + N_TILE - 1) / N_TILE);
-    return launch_pdl(conv_igemm_kernel<N_TILE>, grid, dim3(NTHREADS), C::SMEM_BYTES, st, mapA, mapB, a);
+    return launch_pdl(conv_igemm_kernel<N_TILE>, grid, dim3(IGEMM_THREADS), C::SMEM_BYTES, st, mapA, mapB, a);
 }
 
 template <int N_TILE, int MT>
@@ -940,7 +982,8 @@ static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const f
                     const double l2_bytes = tiles * (a_bytes + o_bytes + (resident ? 0.0 : filt)) + (resident ? ctas * filt : 0.0);
                     // per tap: each issuer warp (one per stacked tile) spends ~220 cycles of bookkeeping + ~75 per MMA; the tensor pipe
                     // needs nt / 2 cycles per MMA of all stacked tiles
-                    const double issue_tap = 220.0 + KGROUPS * (nt / 2 > 75 ? nt / 2 : 75.0), exec_tap = (double)mt * KGROUPS * (nt / 2);
+                    const double issue_one = 220.0 + KGROUPS * (nt / 2 > 75 ? nt / 2 : 75.0), exec_tap = (double)mt * KGROUPS * (nt / 2);
+                    const double issue_tap = mt == 1 ? 0.5 * issue_one + 60.0 : issue_one;   // MT = 1: the issuers take alternate taps
                     const double mma_clk = (double)taps * n_cblk * (issue_tap > exec_tap ? issue_tap : exec_tap);
                     const double ingest_clk = (a_bytes + (resident ? 0.0 : filt)) / 48.0;
                     const double sm_clk = per_cta * (mma_clk > ingest_clk ? mma_clk : ingest_clk) + 3000.0 * per_cta + 4000.0;

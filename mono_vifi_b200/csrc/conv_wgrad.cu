@@ -27,7 +27,8 @@ constexpr int M_TILE = 128;  // couts per CTA (UMMA M)
 constexpr int N_TILE = 32;   // cins per CTA (UMMA N), one 128-byte MN atom
 constexpr int KP = 32;       // pixels per pipeline stage (4 MMAs of K = 8 per tap)
 constexpr int MAX_TAPS = 9;  // taps x 32 columns <= 512 TMEM columns, 4 stages of (16 + 4 taps) KB of shared memory
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 256;  // warp 0 TMA producer, warps 1 / 6 / 7 MMA issuers, warps 2..5 epilogue
+constexpr int MAX_ISSUERS = 3;
 
 struct WgradArgs {
     float* partial;  // [ksplit][taps][Cout_pad128][Cin_pad32]
@@ -67,15 +68,20 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
     const int k_begin = split * per, k_end = min(p.n_patches, k_begin + per);
     const int n_iters = max(0, k_end - k_begin);
     const int kp = p.pw * p.ph;  // pixels per stage
+    // MMA issuers: one thread sustains one tcgen05.mma per ~70 cycles however small the MMA is (an N = 96 MMA is 48 cycles of tensor
+    // work), so the tap groups of a stage -- each with its own accumulator columns -- are dealt to up to three issuing warps: group g
+    // belongs to issuer g % n_issuers.  The order of additions into any accumulator is unchanged (bitwise repeatable results).
+    const int n_groups = p.fuse_row ? taps / p.fuse_row : 1;
+    const int n_issuers = p.fuse_row ? (n_groups < MAX_ISSUERS ? n_groups : MAX_ISSUERS) : 1;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapG);
         tma_prefetch_desc(&mapX);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], n_issuers);   // every issuer commits once per stage
         }
-        mbar_init(tmem_full_bar, 1);
+        mbar_init(tmem_full_bar, n_issuers);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -120,7 +126,9 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
                 if (++px == p.patches_x) { px = 0; if (++py == p.patches_y) { py = 0; ++b; } }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp >= 6) {
+        const int issuer = warp == 1 ? 0 : warp - 5;   // 0, 1, 2
+        if (issuer < n_issuers) {
         // the whole warp runs the (uniform) loop; one elected lane issues
         constexpr uint32_t idesc = make_idesc_tf32(M_TILE, N_TILE, /*A MN-major*/ 1, /*B MN-major*/ 1);
         // MN-major, 32-byte-unit 128B swizzle: 512-byte atoms of (4 pixels x 32 channels); the next 4 pixels +512 B (SBO),
@@ -151,8 +159,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
                     const uint64_t brow = make_smem_desc(0, lbo, 512, SWZ_128B_BASE32B);
                     const uint64_t brow_up = brow & 0xFFFFFFFF00000000ull;
                     const uint32_t brow_lo = (b_lo & 0x3FFFu) | (uint32_t)(brow & 0xFFFFC000ull);
-                    const int groups = taps / p.fuse_row;
-                    for (int kh = 0; kh < groups; ++kh) {
+                    for (int kh = issuer; kh < n_groups; kh += n_issuers) {
                         const uint32_t bt = brow_lo + (uint32_t)(p.shared_patch ? kh * p.pwx * 8 : kh * p.fuse_row * kp * 8);
                         const uint32_t dcol = tmem_d + (uint32_t)(kh * p.fuse_row * N_TILE);
 #pragma unroll 4
@@ -181,6 +188,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
         }
         if (elect_one()) umma_commit(tmem_full_bar);
         __syncwarp();
+        }
     } else {
         // epilogue: thread = one cout row; per tap 32 contiguous cins
         const int q = warp & 3;

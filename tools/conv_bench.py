@@ -28,7 +28,7 @@ for name, B, Cin, H, W, Cout, k, pad, stride in SHAPES:
     gys = [torch.randn(B, Ho, Wo, Cout, device=dev).permute(0, 3, 1, 2) for _ in range(nbuf)]
     flops = 2.0 * B * Ho * Wo * Cout * Cin * k * k
     res = {}
-    for what in ("fprop", "wgrad"):
+    for what in os.environ.get("CONV_BENCH_WHAT", "fprop,wgrad").split(","):
         def run(i):
             if what == "fprop":
                 conv_tc.conv_forward_raw(xs[i % nbuf], wp, None, Cout, k, k, pad, stride)
@@ -56,4 +56,4 @@ for name, B, Cin, H, W, Cout, k, pad, stride in SHAPES:
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / iters
         res[what] = (us, flops / us / 1e6)
-    print("%-32s fprop %7.1f us %6.1f TF/s | wgrad %7.1f us %6.1f TF/s | %.1f GF" % (name, res["fprop"][0], res["fprop"][1], res["wgrad"][0], res["wgrad"][1], flops / 1e9))
+    print("%-32s %s | %.1f GF" % (name, " | ".join("%s %7.1f us %6.1f TF/s" % (k, v[0], v[1]) for k, v in res.items()), flops / 1e9))
