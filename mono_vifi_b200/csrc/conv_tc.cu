@@ -57,6 +57,7 @@ struct ConvArgs {
     int act;                     // 0 none, 1 relu, 2 elu, 3 prelu (per-channel `slope`)
     const float* slope;
     float* dbg;                  // debug: raw copy of pipeline stage 0 (A then B) of CTA (0,0); null in production
+    int single_issuer;           // 1: one MMA issuer (MVF_IGEMM_ISSUERS=1, A/B timing and bisection)
 };
 
 // ---- epilogue arithmetic: v[0..CH) += bias[n_first ..], then the activation ---------------------------------------
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS) conv_igemm_kernel(const __grid_
     const int n_iters = p.KH * p.KW * p.n_cblk;
     // two MMA issuers (see conv_patch_kernel): warp 1 multiplies the even pipeline iterations into accumulator columns [0, N), warp 6
     // the odd ones into [N, 2N); the epilogue adds the two halves (a fixed order, so results stay bitwise repeatable)
-    const int n_issuers = n_iters >= 2 ? 2 : 1;
+    const int n_issuers = (n_iters >= 2 && !p.single_issuer) ? 2 : 1;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA);
@@ -468,6 +469,7 @@ struct PatchArgs {
     int n_mtiles, n_tiles;       // M tiles (B * nseg * tiles_y), all tiles (M tiles x N tiles)
     int b_resident;              // 1: the whole filter bank of the CTA's couts fits in the ring and is loaded ONCE per CTA
     int tma_store;               // 1: epilogue stages slabs in shared memory and stores them with TMA; 0: per-thread stores
+    int no_split;                // MT = 1: 1 = issuer 0 multiplies every tap (MVF_PATCH_SPLIT=0, A/B timing and bisection)
     int dbg;                     // timing experiments only: 4 = no MMAs, 8 = no TMA loads
 };
 
@@ -612,7 +614,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, 1) conv_patch_kernel(const __gr
                     const int ng = (cb == p.n_cblk - 1) ? p.kg_last : KGROUPS;  // all-zero channel groups are not multiplied
                     int kw = 0;
                     for (int tp = 0; tp < taps; ++tp) {
-                        const bool mine = !SPLIT_TAPS || par == my_mt;
+                        const bool mine = !SPLIT_TAPS || (p.no_split ? my_mt == 0 : par == my_mt);
                         par ^= 1;
                         uint32_t b_lo;
                         if (resident) {
@@ -690,7 +692,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, 1) conv_patch_kernel(const __gr
                     float v[SLAB];
 #pragma unroll
                     for (int jj = 0; jj < SLAB; ++jj) v[jj] = __uint_as_float(rr[jj]);
-                    if constexpr (MT == 1) {          // the odd taps' partial sums
+                    if (MT == 1 && !p.no_split) {     // the odd taps' partial sums
                         if constexpr (SLAB == 32) tmem_ld32(taddr + (uint32_t)N_TILE, rr);
                         else tmem_ld16(taddr + (uint32_t)N_TILE, rr);
                         tmem_ld_wait();
@@ -1010,6 +1012,7 @@ static cudaError_t conv_forward_patch(const ConvDesc& d, const float* x, const f
     // the MMAs of the last taps read up to (KW - 1) rows past R*P for positions that are never stored; keep them inside the buffer
     a.patch_stride = ((a.patch_bytes + (d.KW - 1 + TILE_M - a.TR * a.P) * 128) + 1023) / 1024 * 1024;
     a.dbg = getenv("MVF_CONV_DBG") ? atoi(getenv("MVF_CONV_DBG")) : 0;
+    a.no_split = (getenv("MVF_PATCH_SPLIT") && atoi(getenv("MVF_PATCH_SPLIT")) == 0) ? 1 : 0;
     a.n_mtiles = d.B * a.nseg * a.tiles_y;
     a.n_tiles = a.n_mtiles * n_ntiles;
     const int slab = n_tile < 32 ? n_tile : 32;
@@ -1129,6 +1132,7 @@ cudaError_t conv_forward(const ConvDesc& d, const float* x, const float* w_packe
     a.n_cblk = (d.Cin + BLOCK_K - 1) / BLOCK_K;
     a.act = act;
     a.dbg = g_dbg;
+    a.single_issuer = (getenv("MVF_IGEMM_ISSUERS") && atoi(getenv("MVF_IGEMM_ISSUERS")) == 1) ? 1 : 0;
     int n_tile = 16;
     while (n_tile < d.Cout && n_tile < 128) n_tile *= 2;
 
@@ -1253,6 +1257,7 @@ cudaError_t conv_dgrad_s2(const ConvDesc& d, const float* gy, const float* w_pac
     a.n_cblk = (d.Cout + BLOCK_K - 1) / BLOCK_K;  // K = the forward convolution's output channels
     a.act = 0;
     a.dbg = nullptr;
+    a.single_issuer = 0;
     int n_tile = 16;
     while (n_tile < d.Cin && n_tile < 128) n_tile *= 2;
     CUtensorMap mapA, mapB;

@@ -44,6 +44,7 @@ struct WgradArgs {
     int pwx;           // shared patch: its pitch in pixels (pw + KW - 1)
     int stage_bytes, a_bytes, b_bytes;  // stage stride (1024-aligned), bytes landed for A and for B (all taps)
     int stages;        // pipeline depth (2..6), as many as fit in shared memory
+    int max_issuers;   // MMA-issuing warps in use (1..3; MVF_WGRAD_ISSUERS for A/B)
     int g_ragged;      // 1: Cout > 32 and not a multiple of 32 (HRNet's 36 / 72 / 144): mapG is the 4-D (co, ox, oy, b) map, one box per
                        // 32-cout block, channels past Cout zero-filled by TMA
 };
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
     // work), so the tap groups of a stage -- each with its own accumulator columns -- are dealt to up to three issuing warps: group g
     // belongs to issuer g % n_issuers.  The order of additions into any accumulator is unchanged (bitwise repeatable results).
     const int n_groups = p.fuse_row ? taps / p.fuse_row : 1;
-    const int n_issuers = p.fuse_row ? (n_groups < MAX_ISSUERS ? n_groups : MAX_ISSUERS) : 1;
+    const int n_issuers = p.fuse_row ? (n_groups < p.max_issuers ? n_groups : p.max_issuers) : 1;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapG);
@@ -404,6 +405,8 @@ cudaError_t conv_wgrad(const WgradDesc& d, const float* x, const float* gy, floa
     a.Ho = pl.Ho; a.Wo = pl.Wo; a.B = d.B;
     a.pw = pl.pw; a.ph = pl.ph; a.patches_x = pl.patches_x; a.patches_y = pl.patches_y; a.n_patches = pl.n_patches;
     a.stages = pl.stages;
+    a.max_issuers = MAX_ISSUERS;
+    if (const char* e = getenv("MVF_WGRAD_ISSUERS")) a.max_issuers = atoi(e) < 1 ? 1 : (atoi(e) > MAX_ISSUERS ? MAX_ISSUERS : atoi(e));
     a.fuse_row = 0;
     if (!getenv("MVF_WGRAD_NO_FUSE")) {
         if (pl.shared_patch) {

@@ -61,6 +61,7 @@ def main():
     torch.cuda.synchronize()
     worst, worst_name, n = 0.0, None, 0
     num = den = 0.0
+    per_param = []
     for (name_s, mod_s), (name_d, mod_d) in zip(m_s.items(), m_d.items()):
         for (pn, ps), (_, pd) in zip(mod_s.named_parameters(), mod_d.named_parameters()):
             if ps.grad is None:
@@ -72,6 +73,11 @@ def main():
             scale = float(ps.grad.abs().max())
             if scale > 0:
                 e = float((g - ps.grad).abs().max()) / scale
+                per_param.append((e, "%s.%s" % (name_s, pn)))
+                if os.environ.get("MVF_DDP_DEBUG") and pn.endswith("layer4.1.conv2.weight") and rank == 0:
+                    print("DEBUG %s.%s single: norm %.9g first %s | dp: norm %.9g first %s" % (
+                        name_s, pn, float(ps.grad.double().norm()), [round(float(v), 9) for v in ps.grad.flatten()[:3]],
+                        float(g.double().norm()), [round(float(v), 9) for v in g.flatten()[:3]]), flush=True)
                 if e > worst:
                     worst, worst_name = e, "%s.%s" % (name_s, pn)
             num += float((g - ps.grad).double().pow(2).sum())
@@ -117,7 +123,8 @@ def main():
             w_spread = max(w_spread, float((hi - lo).abs().max()))
     if rank == 0:
         print(json.dumps({"world": world, "multi_frame": multi, "sync_bn_modules": n_sync, "params_compared": n,
-                          "grad_worst_rel": worst, "grad_worst_name": worst_name, "grad_rel_l2": (num / max(den, 1e-30)) ** 0.5,
+                          "grad_worst_rel": worst, "grad_worst_name": worst_name,
+                          "grad_worst_five": [[round(e, 6), nm] for e, nm in sorted(per_param, reverse=True)[:5]], "grad_rel_l2": (num / max(den, 1e-30)) ** 0.5,
                           "buffer_rel_err_vs_single": buf_err, "buffer_spread_across_ranks": buf_spread,
                           "loss_single": float(out_s["loss"]), "loss_dp_mean": float(loss_d),
                           "weight_spread_after_step": w_spread, "peer_exchanges": peer.exchanges,

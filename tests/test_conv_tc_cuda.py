@@ -259,3 +259,41 @@ def test_dispconv_direct_kernels_vs_fp64(case):
     xp.grad = None
     conv_tc.conv2d(xp, w, b, 1, 0).backward(gy)
     assert torch.equal(gw1, w.grad)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 12, 40, 64, 3, 1), (2, 512, 2, 3, 512, 3, 1), (6, 512, 2, 3, 512, 3, 1), (3, 128, 24, 80, 128, 3, 1),
+                                   (2, 16, 16, 64, 16, 3, 1), (2, 256, 6, 20, 256, 3, 0), (12, 512, 2, 3, 256, 3, 1)])
+def test_every_tile_shape_of_the_patch_kernel(shape):
+    """The stride-1 kernel's tile shape (N_TILE x MT stacked tiles; MT = 1 splits the taps over the two MMA issuers) is picked by a cost
+    model; every shape it can pick must give the same convolution (MVF_CONV_TILE_RULE forces one)."""
+    import torch
+    from mono_vifi_b200 import conv_tc
+    B, Cin, H, W, Cout, k, pad = shape
+    g = torch.Generator(device="cuda").manual_seed(23)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).permute(0, 3, 1, 2)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    ref = _ref(x, w, b, pad)
+    wp = conv_tc.pack_filters(w)
+    n_wide = 16
+    while n_wide < Cout and n_wide < 128:
+        n_wide *= 2
+    old = os.environ.get("MVF_CONV_TILE_RULE")
+    try:
+        outs = {}
+        for rule in [None, "r1"] + ["%d,%d" % (n, mt) for n in (16, 32, 64, 128) if n <= n_wide for mt in (1, 2)]:
+            if rule is None:
+                os.environ.pop("MVF_CONV_TILE_RULE", None)
+            else:
+                os.environ["MVF_CONV_TILE_RULE"] = rule
+            for rep in range(3):   # repeated launches: the issuers' barrier phases wrap differently from call to call
+                y = conv_tc.conv_forward_raw(x, wp, b, Cout, k, k, pad, 1)
+            torch.cuda.synchronize()
+            err = (y - ref).abs().max().item()
+            assert err <= 2e-3 * ref.abs().max().item(), (rule, err, ref.abs().max().item())
+            outs[rule] = y
+    finally:
+        if old is None:
+            os.environ.pop("MVF_CONV_TILE_RULE", None)
+        else:
+            os.environ["MVF_CONV_TILE_RULE"] = old
