@@ -54,6 +54,7 @@ struct __align__(16) BwdSmem {
     float2 GS[H1][W1];        // selection weight of each window {k=0, k=1}
     float D[H1][W1];          // disparity at tile + 1
     float cst[36];
+    float uni[8];             // CTA-uniform scalars computed once by one thread: {gn, cxn, cyn, den, shift}
     int is_last;
 };
 static_assert(sizeof(float) * 24 * NT <= sizeof(float2) * 3 * 3 * H1 * W1, "reduction scratch aliases CF");
@@ -138,6 +139,20 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
     if (tid < 12) sm.cst[tid] = a.inv_K[16 * b + tid];
     else if (tid < 24) sm.cst[tid] = a.P0[12 * b + tid - 12];
     else if (tid < 36) sm.cst[tid] = a.P1[12 * b + tid - 24];
+    else if (tid == 36) {
+        // normalisation constants (double conversions, divisions and the three dependent loads of the forward's statistics) once per
+        // CTA instead of once per thread: they were 11 % of the kernel's stall samples (profiles/r1_f1_bwd_ncu_lines.txt, line 273)
+        const float mean = a.stats[4 * b + 0], Sx = a.stats[4 * b + 1], Sy = a.stats[4 * b + 2];
+        const float den = mean + 1e-7f;
+        const float cxn = gout * a.smooth_w / (float)((double)B * H * (W - 1));
+        const float cyn = gout * a.smooth_w / (float)((double)B * (H - 1) * W);
+        const float dotb = cxn * Sx + cyn * Sy;  // sum_q g_nd[q] * disp[q]
+        sm.uni[0] = gout / (float)((double)B * (double)HW);
+        sm.uni[1] = cxn;
+        sm.uni[2] = cyn;
+        sm.uni[3] = den;
+        sm.uni[4] = dotb / (den * den * (float)HW);
+    }
     __syncthreads();
 
     const float* dispb = a.disp + (size_t)b * HW;
@@ -151,7 +166,7 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
     // ---------------- phase 1 ---------------------------------------------------------------------------------
     {
         const int first_rep = am ? (avg ? 1 : 2) : 0;
-        const float gn = gout / (float)((double)B * (double)HW);
+        const float gn = sm.uni[0];
         for (int p = tid; p < H2 * W2; p += NT) {
             int hy = p / W2, hx = p - hy * W2;
             int ry = ty0 - 2 + hy, rx = tx0 - 2 + hx;
@@ -268,12 +283,7 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
             }
         }
         // smoothness constants (train.py:1044-1049, layers.py:231-242)
-        const float mean = a.stats[4 * b + 0], Sx = a.stats[4 * b + 1], Sy = a.stats[4 * b + 2];
-        const float den = mean + 1e-7f;
-        const float cxn = gout * a.smooth_w / (float)((double)B * H * (W - 1));
-        const float cyn = gout * a.smooth_w / (float)((double)B * (H - 1) * W);
-        const float dotb = cxn * Sx + cyn * Sy;  // sum_q g_nd[q] * disp[q]
-        const float shift = dotb / (den * den * (float)HW);
+        const float cxn = sm.uni[1], cyn = sm.uni[2], den = sm.uni[3], shift = sm.uni[4];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int col = 2 * cp + j, x = tx0 + col;

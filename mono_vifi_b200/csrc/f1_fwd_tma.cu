@@ -9,7 +9,7 @@
 //   * warp 0 (producer) stages the dense inputs of a tile -- disparity, target, both sources with a 1-px halo, tie-break
 //     noise, mask: everything that is NOT a data-dependent gather, 40 of the 48 algorithmic bytes per pixel -- with TMA box
 //     loads (cp.async.bulk.tensor, zero fill outside the image) into a shared-memory slot behind an mbarrier;
-//   * 5 gather warps complete the slot: reflection padding of the staged planes on border tiles, projection of every halo
+//   * 4 gather warps complete the slot: reflection padding of the staged planes on border tiles, projection of every halo
 //     position (bit-exact coordinate chain of common.cuh), 24 bilinear corner loads per position through L1, warped
 //     candidates stored as float2 {warp0, warp1} for packed FFMA2;
 //   * 4 SSIM warps consume the slot: separable 3x3 window sums straight from the staged planes (register ring), SSIM + L1
@@ -35,12 +35,21 @@ constexpr int TW = 32, TH = 16;
 constexpr int HWD = TW + 2, HHT = TH + 2;   // tile + 1-px halo
 constexpr int SWD = TW + 8;                 // staged row: [tx0 - 4, tx0 + TW + 4), 16-byte aligned start
 constexpr int NPOSN = HHT * HWD;            // 612 halo positions
-constexpr int NG = 5, NS = 4;               // gather / SSIM warps
+// Role sizes, measured at B12 192x640 (profiles/r2_f1_variants.md): the SSIM warps are the critical role and every additional gather
+// warp takes issue slots from them -- 4 gather warps (5 rounds over the halo positions) 80.8 us, 5 (4 rounds) 87.3, 7 (3 rounds) 97,
+// 3 (7 rounds: the gathers become critical) 99.9; twice the SSIM warps with half the rows each (MVF_F1_RPT=4) 86.
+#ifndef MVF_F1_NG
+#define MVF_F1_NG 4
+#endif
+#ifndef MVF_F1_RPT
+#define MVF_F1_RPT 8
+#endif
+constexpr int RPT = MVF_F1_RPT;             // output rows per SSIM thread
+constexpr int NG = MVF_F1_NG, NS = 2 * (16 / RPT);   // gather / SSIM warps (one SSIM thread per (pass, column, group of RPT rows))
 constexpr int NSLOT = 2;                    // pipeline depth (tiles in flight per CTA)
 constexpr int NGT = NG * 32, NST = NS * 32;
 constexpr int NT = 32 * (1 + NG + NS);
 constexpr int NROUND = (NPOSN + NGT - 1) / NGT;   // halo positions per gather thread
-constexpr int RPT = 8;                      // output rows per SSIM thread
 constexpr int CST_MAXB = 32;                // images whose matrices are kept in shared memory (others: per-tile reload)
 constexpr int HOFF = 3;                     // staged column of halo column 0 (x = tx0 - 1)
 static_assert(NST == 2 * TW * (TH / RPT), "one (pass, column, row group) item per SSIM thread");
@@ -185,8 +194,11 @@ __global__ void __launch_bounds__(NT, 2) f1_fwd_tma_kernel(const F1Args a, const
                                                            const int tiles_y, const int n_tiles_, const int nid_loaded,
                                                            const uint32_t tx_bytes, const int dbg_mode) {
     const int n_tiles = (dbg_mode & 64) ? 0 : n_tiles_;   // timing experiment: launch + prologue + epilogue only
-    extern __shared__ unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // The declared alignment -- not an integer round-up of the pointer -- keeps the shared address space visible to the compiler:
+    // every access below is an LDS / STS with an immediate offset.  The round-up (round 2's first version) turned all 300 of them into
+    // generic 64-bit LD / ST with their own address arithmetic: 95.7 -> 87.3 us for this change alone.
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = a.H, W = a.W;
     const int HWi = H * W;
@@ -584,7 +596,8 @@ cudaError_t launch_f1_forward_tma(const F1Args& a, cudaStream_t stream) {
     if (ok && a.mask) ok = encode_planes(enc, &maps.mask, a.mask, a.B, a.H, a.W, TW, TH, 1);
     if (!ok) return cudaErrorInvalidValue;
     const uint32_t tx = (uint32_t)(10 * HHT * SWD * 4 + nid * TH * TW * 4 + (a.mask ? TH * TW * 4 : 0));
-    const size_t smem = sizeof(Smem) + 128;
+    const size_t smem = sizeof(Smem);
+    static_assert(2 * (sizeof(Smem) + 1024) <= 228 * 1024, "two CTAs per SM");
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(f1_fwd_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
