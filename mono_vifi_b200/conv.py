@@ -8,8 +8,10 @@ unchanged, and routes the arithmetic through `conv2d()`:
   backend "cudnn"    torch's F.conv2d (cuDNN, a LIBRARY baseline -- what the reference itself runs on), kept for
                      A/B timing (MVF_CONV_BACKEND=cudnn) and for CPU tensors (the host-side tests).
 
-Every call is counted in `stats` so the bench can report how much of the conv work ran on which path; shapes the
-tcgen05 kernels do not cover are routed to cuDNN and show up there -- never silently.
+Every call is counted in `stats` so the bench can report how much of the conv work ran on which path.  A CUDA tensor
+whose shape the tcgen05 kernels do not cover (grouped or dilated convolutions, asymmetric padding, strides above 2) RAISES
+`UnsupportedConvolution`: the product path has no library fallback.  MVF_LIBRARY_FALLBACK=1 turns the error into a counted
+cuDNN call (porting aid for other architectures; none of the five BASELINE configurations needs it).
 """
 import os
 
@@ -18,7 +20,20 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 _backend = os.environ.get("MVF_CONV_BACKEND", "tcgen05")
+library_fallback = os.environ.get("MVF_LIBRARY_FALLBACK", "0") == "1"
 stats = {"tcgen05": 0, "cudnn": 0}
+
+
+class UnsupportedConvolution(RuntimeError):
+    pass
+
+
+def require_fallback(what):
+    """Called where a shape would leave the tcgen05 kernels: raises unless the counted library fallback was asked for."""
+    if not library_fallback:
+        raise UnsupportedConvolution("%s is not covered by the tcgen05 convolution kernels and the product path has no library "
+                                     "fallback (MVF_LIBRARY_FALLBACK=1 allows a counted cuDNN call; MVF_CONV_BACKEND=cudnn runs "
+                                     "the whole network on the library for A/B timing)" % what)
 
 
 def set_backend(name):
@@ -63,6 +78,8 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, act=
                 bias = None if bias is None else F.pad(bias, (0, extra))
                 return conv_tc.conv2d(x, weight, bias, stride, padding, act=act)[:, :cout]
             return conv_tc.conv2d(x, weight, bias, stride, padding, act=act)
+        require_fallback("conv2d(x=%s, weight=%s, stride=%s, padding=%s, dilation=%s, groups=%s)" %
+                         (tuple(x.shape), tuple(weight.shape), stride, padding, dilation, groups))
     stats["cudnn"] += 1
     return _activate(F.conv2d(x, weight, bias, stride, padding, dilation, groups), act)
 

@@ -417,6 +417,8 @@ def input_grad_s2(x, gy, weight, pad):
 def input_grad_library(x, gy, weight, pad, stride):
     """dL/dx of the shapes the tcgen05 dgrad does not cover yet (strided convolutions): cuDNN, counted in conv.stats."""
     from . import conv
+    if os.environ.get("MVF_DGRAD_S2", "1") != "0":   # (MVF_DGRAD_S2=0 is the explicit A/B switch to the library)
+        conv.require_fallback("data gradient of conv2d(x=%s, weight=%s, stride=%s, padding=%s)" % (tuple(x.shape), tuple(weight.shape), stride, pad))
     conv.stats["cudnn_dgrad"] = conv.stats.get("cudnn_dgrad", 0) + 1
     gx, _, _ = torch.ops.aten.convolution_backward(gy, x, weight, None, list(_pair(stride)), [pad, pad], [1, 1], False, [0, 0], 1,
                                                    [True, False, False])
@@ -456,6 +458,7 @@ def weight_grad(x, gy, wshape, pad, stride=1):
                    "mvf_conv2d_wgrad")
         return gw
     from . import conv
+    conv.require_fallback("weight gradient of conv2d(x=%s, weight=%s, stride=%s, padding=%s)" % (tuple(x.shape), tuple(wshape), stride, pad))
     conv.stats["cudnn_wgrad"] = conv.stats.get("cudnn_wgrad", 0) + 1
     w = torch.empty(wshape, device=x.device, dtype=x.dtype).contiguous(memory_format=torch.channels_last)
     _, gw, _ = torch.ops.aten.convolution_backward(gy, x, w, None, list(_pair(stride)), [pad, pad], [1, 1], False, [0, 0], 1,

@@ -297,3 +297,25 @@ def test_every_tile_shape_of_the_patch_kernel(shape):
             os.environ.pop("MVF_CONV_TILE_RULE", None)
         else:
             os.environ["MVF_CONV_TILE_RULE"] = old
+
+
+def test_shapes_outside_the_kernels_raise_instead_of_reaching_a_library():
+    """The product path has no silent (nor default) library fallback: a CUDA convolution the tcgen05 kernels do not cover raises;
+    MVF_LIBRARY_FALLBACK=1 (conv.library_fallback) turns it into a counted cuDNN call."""
+    import torch
+    from mono_vifi_b200 import conv
+    x = torch.randn(2, 8, 12, 16, device="cuda")
+    w = torch.randn(8, 4, 3, 3, device="cuda")          # groups = 2
+    assert conv.get_backend() == "tcgen05" and not conv.library_fallback
+    with pytest.raises(conv.UnsupportedConvolution):
+        conv.conv2d(x, w, None, 1, 1, 1, 2)
+    with pytest.raises(conv.UnsupportedConvolution):
+        conv.conv2d(x, torch.randn(8, 8, 3, 3, device="cuda"), None, 1, 2, 2, 1)   # dilation 2
+    n0 = conv.stats["cudnn"]
+    conv.library_fallback = True
+    try:
+        y = conv.conv2d(x, w, None, 1, 1, 1, 2)
+    finally:
+        conv.library_fallback = False
+    assert conv.stats["cudnn"] == n0 + 1
+    assert torch.allclose(y, torch.nn.functional.conv2d(x, w, None, 1, 1, 1, 2))

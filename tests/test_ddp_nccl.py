@@ -30,7 +30,13 @@ def test_data_parallel_step_equals_single_process_on_the_global_batch(mode):
     assert out["sync_bn_modules"] >= 40
     # fp32-class arithmetic on both sides; the orders of the batch reductions differ (two shards vs one batch)
     assert out["grad_rel_l2"] <= 2e-4, out             # measured 2e-5 .. 4e-5
-    assert out["grad_worst_rel"] <= 1e-3, out          # measured 1e-4
+    # worst entry of any parameter's gradient, relative to that gradient's largest entry -- with the yardstick floored at 1e-3 of the
+    # network's largest gradient entry: a parameter whose whole gradient sits four orders of magnitude below its network's is a sum
+    # that cancels to rounding level (encoder layer4's 512x512x3x3 filters on the 2x3 map of this 64x96 case: norm 8e-5), and any
+    # change of summation order -- two shards instead of one batch, or another MMA-issuer split -- moves it by ~1e-2 of ITS scale
+    # (tools/conv_exact.py: the convolutions themselves are bit-exact on integer data for every tile shape and issuer split)
+    assert out["grad_worst_rel_floored"] <= 1e-3, out  # measured 1e-4 (single-frame), 5e-5 (multi-frame)
+    assert out["grad_worst_rel"] <= 3e-2, out          # measured 1e-4 / 8e-3 (the layer4 filters above)
     assert out["buffer_rel_err_vs_single"] <= 1e-4, out
     assert out["buffer_spread_across_ranks"] == 0.0, out       # identical bits on every rank
     assert abs(out["loss_single"] - out["loss_dp_mean"]) <= 1e-4 * abs(out["loss_single"]), out
