@@ -87,7 +87,12 @@ __global__ void __launch_bounds__(NT) bn_partial_kernel(const float4* __restrict
 // (cl, bl) adds blocks bl, bl + FIN_BL, ... of channel c0 + cl -- for a given block the 32 channels are one coalesced 128-byte read
 // (round 1 had one warp per channel whose lanes read 32 different cache lines per load: 6-15 us per launch, on the critical path of
 // every BatchNorm) -- and the FIN_BL partial sums meet in shared memory.  Returns true in the thread that holds the result.
-constexpr int FIN_BL = 8;
+// The kernel is a pure latency chain (a 64-channel layer launches TWO CTAs), so the walk over the blocks is as short and as wide as it
+// gets: 32 block lanes (1024 threads) and four blocks per trip with their loads issued together.  With 8 lanes and one block per trip a
+// thread made 45 dependent round trips to L2 for 360 blocks: 32 us per launch under ncu (17 us in the step, profiles/r2_launches_summary.txt),
+// 120 launches per step, each between a BatchNorm's statistics and its apply kernel.
+constexpr int FIN_BL = 32;
+constexpr int FIN_UNROLL = 4;
 __device__ __forceinline__ bool channel_sums(const float* __restrict__ partial, int nblocks, int C, int fold, int& c, double& s, double& ss) {
     __shared__ double red[FIN_BL][2][32];
     const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
@@ -96,16 +101,31 @@ __device__ __forceinline__ bool channel_sums(const float* __restrict__ partial, 
     s = 0.0;
     ss = 0.0;
     if (c < C)
-        for (int b = bl; b < nblocks; b += FIN_BL)
-            for (int j = 0; j < fold; ++j) {
-                s += (double)partial[(size_t)b * 2 * Cv + j * C + c];
-                ss += (double)partial[(size_t)b * 2 * Cv + Cv + j * C + c];
+        for (int b0 = bl; b0 < nblocks; b0 += FIN_UNROLL * FIN_BL) {
+            float v[FIN_UNROLL][2][2];
+#pragma unroll
+            for (int u = 0; u < FIN_UNROLL; ++u) {
+                const int b = b0 + u * FIN_BL;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const bool ok = b < nblocks && j < fold;
+                    v[u][j][0] = ok ? partial[(size_t)b * 2 * Cv + j * C + c] : 0.f;
+                    v[u][j][1] = ok ? partial[(size_t)b * 2 * Cv + Cv + j * C + c] : 0.f;
+                }
             }
+#pragma unroll
+            for (int u = 0; u < FIN_UNROLL; ++u)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {   // (fold <= 2; the slots past it hold zeros)
+                    s += (double)v[u][j][0];
+                    ss += (double)v[u][j][1];
+                }
+        }
     red[bl][0][cl] = s;
     red[bl][1][cl] = ss;
     __syncthreads();
     if (bl != 0 || c >= C) return false;
-#pragma unroll
+#pragma unroll 4
     for (int q = 1; q < FIN_BL; ++q) {
         s += red[q][0][cl];
         ss += red[q][1][cl];
@@ -118,7 +138,7 @@ __device__ __forceinline__ bool channel_sums(const float* __restrict__ partial, 
 // kernels apply; "virtual" channel j * C + c is real channel c at pixels of parity j.  The partial sums of the fold virtual channels of a
 // real channel are added here, mean / invstd (and copies of gamma / beta) are written for every virtual channel, the running
 // statistics once per real channel.  C is the REAL channel count, P the real pixel count.
-__global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int nblocks, int C, long long P, float eps, float momentum,
+__global__ void __launch_bounds__(32 * FIN_BL) bn_finalize_fwd_kernel(const float* __restrict__ partial, int nblocks, int C, long long P, float eps, float momentum,
                                        float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
                                        float* __restrict__ running_var, long long* __restrict__ num_batches_tracked, int fold,
                                        const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ gamma_v,
@@ -148,7 +168,7 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int nb
 
 // backward: d_beta = sum g, d_gamma = sum g * xhat (fold: summed over the virtual channels of a real channel; per-virtual-channel
 // copies of d_gamma / d_beta / gamma for the apply kernel)
-__global__ void bn_finalize_bwd_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ dgamma,
+__global__ void __launch_bounds__(32 * FIN_BL) bn_finalize_bwd_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, int fold, const float* __restrict__ gamma, float* __restrict__ dgamma_v,
                                        float* __restrict__ dbeta_v, float* __restrict__ gamma_v) {
     pdl_sync();
@@ -280,7 +300,7 @@ __global__ void bias_finalize_kernel(const float* __restrict__ partial, int nblo
 //   forward : sum_0 = sum x, sum_1 = sum x^2      -> mean, biased variance over the global count
 //   backward: sum_0 = sum g, sum_1 = sum g * xhat -> the two means of the input gradient over the global count; the
 //             parameter gradients d_beta / d_gamma stay LOCAL sums (they are averaged with all other gradients later).
-__global__ void bn_sums_kernel(const float* __restrict__ partial, int nblocks, int C, double count, double* __restrict__ sums,
+__global__ void __launch_bounds__(32 * FIN_BL) bn_sums_kernel(const float* __restrict__ partial, int nblocks, int C, double count, double* __restrict__ sums,
                                float* __restrict__ local0, float* __restrict__ local1) {
     pdl_sync();
     if (blockIdx.x == 0 && threadIdx.x == 0) sums[2 * C] = count;
