@@ -422,7 +422,7 @@ def run_ours(args):
     for tag, (fl, sec, n) in sorted(ct.items()):
         ach = fl / sec / 1e12 if sec > 0 else 0.0
         conv_roof[tag] = {"kernel": "conv_%s (tcgen05, tf32)" % tag, "bound": "tensor", "achieved": ach, "peak": tf32_peak,
-                          "unit": "TFLOP/s", "frac": ach / tf32_peak, "launches_timed": n, "flop_per_step": fl / n_eager,
+                          "unit": "TFLOP/s", "frac": ach / tf32_peak, "launches_timed": n, "launches_per_step": n // n_eager, "flop_per_step": fl / n_eager,
                           "ms_per_step": 1e3 * sec / n_eager,
                           "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 dense rate is half of bf16)"}
     line = {"metric": METRIC, "value": args.batch * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world,

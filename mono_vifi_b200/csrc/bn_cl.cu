@@ -190,7 +190,7 @@ __global__ void bn_apply_fwd_kernel(const float4* __restrict__ x, const float4* 
                                     const float* __restrict__ beta, long long total4, int C4, int relu) {
     pdl_sync();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C4);
+        const int c = total4 < 0xffffffffLL ? (int)((unsigned)i % (unsigned)C4) : (int)(i % C4);
         const float4 m = *reinterpret_cast<const float4*>(mean + 4 * c), is = *reinterpret_cast<const float4*>(invstd + 4 * c);
         const float4 ga = *reinterpret_cast<const float4*>(gamma + 4 * c), be = *reinterpret_cast<const float4*>(beta + 4 * c);
         const float4 v = __ldg(x + i);
@@ -212,7 +212,7 @@ __global__ void bn_apply_bwd_kernel(const float4* __restrict__ x, const float4* 
                                     const float* __restrict__ dbeta, long long total4, int C4, float inv_P, int relu) {
     pdl_sync();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C4);
+        const int c = total4 < 0xffffffffLL ? (int)((unsigned)i % (unsigned)C4) : (int)(i % C4);
         const float4 m = *reinterpret_cast<const float4*>(mean + 4 * c), is = *reinterpret_cast<const float4*>(invstd + 4 * c);
         const float4 ga = *reinterpret_cast<const float4*>(gamma + 4 * c);
         const float4 dg = *reinterpret_cast<const float4*>(dgamma + 4 * c), db = *reinterpret_cast<const float4*>(dbeta + 4 * c);
@@ -352,7 +352,7 @@ __global__ void bn_apply_bwd_sync_kernel(const float4* __restrict__ x, const flo
     pdl_sync();
     const float inv_P = *inv_count;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C4);
+        const int c = total4 < 0xffffffffLL ? (int)((unsigned)i % (unsigned)C4) : (int)(i % C4);
         const float4 m = *reinterpret_cast<const float4*>(mean + 4 * c), is = *reinterpret_cast<const float4*>(invstd + 4 * c);
         const float4 ga = *reinterpret_cast<const float4*>(gamma + 4 * c);
         const float4 dg = *reinterpret_cast<const float4*>(dgamma + 4 * c), db = *reinterpret_cast<const float4*>(dbeta + 4 * c);

@@ -9,6 +9,24 @@
 namespace mvf {
 namespace {
 
+// i -> (i0, i1, i2, i3) with i = ((i3 * n2 + i2) * n1 + i1) * n0 + i0.  32-bit arithmetic whenever the tensor allows it: the 64-bit
+// div / mod chains (three of each per element) cost more instructions than the rest of these kernels.
+__device__ __forceinline__ void split4(long long i, bool small, int n0, int n1, int n2, int& i0, int& i1, int& i2, int& i3) {
+    if (small) {
+        unsigned r = (unsigned)i;
+        i0 = (int)(r % (unsigned)n0); r /= (unsigned)n0;
+        i1 = (int)(r % (unsigned)n1); r /= (unsigned)n1;
+        i2 = (int)(r % (unsigned)n2);
+        i3 = (int)(r / (unsigned)n2);
+    } else {
+        long long r = i;
+        i0 = (int)(r % n0); r /= n0;
+        i1 = (int)(r % n1); r /= n1;
+        i2 = (int)(r % n2);
+        i3 = (int)(r / n2);
+    }
+}
+
 __device__ __forceinline__ int reflect1i(int i, int n) {  // index map of ReflectionPad2d(1): -1 -> 1, n -> n-2
     i = i < 0 ? -i : i;
     return i >= n ? 2 * n - 2 - i : i;
@@ -22,11 +40,8 @@ __global__ void upcat_pad_fwd_kernel(const float4* __restrict__ a, const float4*
     const long long total = (long long)B * Hp * Wp * C4;
     const int Ha = up ? H / 2 : H, Wa = up ? W / 2 : W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C4);
-        long long r = i / C4;
-        const int px = (int)(r % Wp);
-        r /= Wp;
-        const int py = (int)(r % Hp), b = (int)(r / Hp);
+        int c, px, py, b;
+        split4(i, total < 0xffffffffLL, C4, Wp, Hp, c, px, py, b);
         const int sy = reflect1i(py - 1, H), sx = reflect1i(px - 1, W);
         float4 v;
         if (c < Ca4) {
@@ -67,11 +82,8 @@ __global__ void upcat_pad_bwd_a_kernel(const float4* __restrict__ gy, float4* __
     const int Ha = up ? H / 2 : H, Wa = up ? W / 2 : W;
     const long long total = (long long)B * Ha * Wa * Ca4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % Ca4);
-        long long r = i / Ca4;
-        const int ax = (int)(r % Wa);
-        r /= Wa;
-        const int ay = (int)(r % Ha), b = (int)(r / Ha);
+        int c, ax, ay, b;
+        split4(i, total < 0xffffffffLL, Ca4, Wa, Ha, c, ax, ay, b);
         const long long img = (long long)b * Hp * Wp;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const int n = up ? 2 : 1;
@@ -89,17 +101,16 @@ __global__ void upcat_pad_bwd_skip_kernel(const float4* __restrict__ gy, float4*
     const int C4 = Ca4 + Cs4, Hp = H + 2, Wp = W + 2;
     const long long total = (long long)B * H * W * Cs4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % Cs4);
-        long long r = i / Cs4;
-        const int sx = (int)(r % W);
-        r /= W;
-        const int sy = (int)(r % H), b = (int)(r / H);
+        int c, sx, sy, b;
+        split4(i, total < 0xffffffffLL, Cs4, W, H, c, sx, sy, b);
         gs[i] = pad_adjoint(gy, (long long)b * Hp * Wp, C4, Ca4 + c, H, W, sy, sx);
     }
 }
 
 }  // namespace
 
+// 16 CTAs per SM and a grid-stride loop.  (One element per thread -- every load of the kernel in flight at once -- was measured: the
+// step got 0.07 ms SLOWER, the large grids crowd out the kernels of the concurrent streams.)
 static int grid_for(long long total) {
     long long b = (total + 255) / 256;
     return (int)(b < 148 * 16 ? (b < 1 ? 1 : b) : 148 * 16);
@@ -137,11 +148,8 @@ __global__ void maxpool3s2_fwd_kernel(const float4* __restrict__ x, float4* __re
     pdl_sync();
     const long long total = (long long)B * Ho * Wo * C4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C4);
-        long long r = i / C4;
-        const int ox = (int)(r % Wo);
-        r /= Wo;
-        const int oy = (int)(r % Ho), b = (int)(r / Ho);
+        int c, ox, oy, b;
+        split4(i, total < 0xffffffffLL, C4, Wo, Ho, c, ox, oy, b);
         float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         uchar4 k = make_uchar4(0, 0, 0, 0);
 #pragma unroll
@@ -170,11 +178,8 @@ __global__ void maxpool3s2_bwd_kernel(const float4* __restrict__ gy, const uchar
     pdl_sync();
     const long long total = (long long)B * H * W * C4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C4);
-        long long r = i / C4;
-        const int ix = (int)(r % W);
-        r /= W;
-        const int iy = (int)(r % H), b = (int)(r / H);
+        int c, ix, iy, b;
+        split4(i, total < 0xffffffffLL, C4, W, H, c, ix, iy, b);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         // windows (oy, ox) with 2*oy - 1 + dy == iy, dy in 0..2
         for (int oy = (iy + 1) / 2 - ((iy & 1) ? 1 : 0); oy <= (iy + 1) / 2; ++oy) {
