@@ -63,6 +63,7 @@ def main():
     worst_net, worst_net_name = 0.0, None
     num = den = 0.0
     per_param = []
+    per_param_l2 = []
     for (name_s, mod_s), (name_d, mod_d) in zip(m_s.items(), m_d.items()):
         # the largest gradient entry of this network: the yardstick for parameters whose own gradient is orders of magnitude smaller
         # (their entries are sums that cancel to rounding level, e.g. the last ResNet block's 512x512x3x3 filters on a 2x3 map)
@@ -87,6 +88,8 @@ def main():
                 e_net = float((g - ps.grad).abs().max()) / max(scale, 1e-3 * net_scale)
                 if e_net > worst_net:
                     worst_net, worst_net_name = e_net, "%s.%s" % (name_s, pn)
+                l2 = float((g - ps.grad).double().norm()) / max(float(ps.grad.double().norm()), 1e-30)
+                per_param_l2.append((l2, "%s.%s" % (name_s, pn), scale, net_scale))
             num += float((g - ps.grad).double().pow(2).sum())
             den += float(ps.grad.double().pow(2).sum())
             n += 1
@@ -132,6 +135,8 @@ def main():
         print(json.dumps({"world": world, "multi_frame": multi, "sync_bn_modules": n_sync, "params_compared": n,
                           "grad_worst_rel": worst, "grad_worst_name": worst_name,
                           "grad_worst_rel_floored": worst_net, "grad_worst_floored_name": worst_net_name,
+                          "grad_worst_param_rel_l2": max(per_param_l2)[0] if per_param_l2 else 0.0,
+                          "grad_worst_five_rel_l2": [[float("%.3g" % e), nm, float("%.3g" % sc), float("%.3g" % ns)] for e, nm, sc, ns in sorted(per_param_l2, reverse=True)[:5]],
                           "grad_worst_five": [[round(e, 6), nm] for e, nm in sorted(per_param, reverse=True)[:5]], "grad_rel_l2": (num / max(den, 1e-30)) ** 0.5,
                           "buffer_rel_err_vs_single": buf_err, "buffer_spread_across_ranks": buf_spread,
                           "loss_single": float(out_s["loss"]), "loss_dp_mean": float(loss_d),
