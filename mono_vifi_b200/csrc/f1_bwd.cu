@@ -55,7 +55,6 @@ struct __align__(16) BwdSmem {
     float D[H1][W1];          // disparity at tile + 1
     float cst[36];
     float uni[8];             // CTA-uniform scalars computed once by one thread: {gn, cxn, cyn, den, shift}
-    int is_last;
 };
 static_assert(sizeof(float) * 24 * NT <= sizeof(float2) * 3 * 3 * H1 * W1, "reduction scratch aliases CF");
 
@@ -368,26 +367,21 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
                           (unsigned long long)to_fix(dv));
             }
         }
-        if (lane == 0) __threadfence();  // one release fence per warp, after its last accumulator update
     }
-    __syncthreads();
-    if (tid == 0) {
-        unsigned int total = gridDim.x * gridDim.y * gridDim.z;
-        unsigned int ticket = atomicAdd(&a.ws->counter_bwd, 1u);
-        sm.is_last = (ticket == total - 1);
-    }
-    __syncthreads();
-    if (sm.is_last) {
-        __threadfence();
-        for (int i = tid; i < 24 * B; i += NT) {
-            volatile long long* v = acc + i;
-            double val = from_fix(*v);
-            *v = 0;
-            int k = i / (12 * B), e = i - k * 12 * B;
-            (k == 0 ? a.g_P0 : a.g_P1)[e] = (float)val;
-        }
-        if (tid == 0) a.ws->counter_bwd = 0;
-        __threadfence();
+    // (no fence, no last-CTA ticket: the fixed-point sums are turned into the outputs by f1_bwd_finalize_kernel, the next launch on the
+    // stream.  The fence -- it waits for this warp's atomics to reach L2 -- and the ticket cost every one of the 2880 CTAs two block
+    // barriers and ~6 % of the kernel's stall samples, profiles/r2_f1_bwd_final.keys.txt.)
+}
+
+// [2][B][12] fixed-point sums -> grad_P0 / grad_P1, and the accumulators are zeroed for the next launch (self-cleaning workspace)
+__global__ void f1_bwd_finalize_kernel(const F1Args a) {
+    long long* acc = ws_bwd_acc(a.ws, a.B);
+    const int B = a.B;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 24 * B; i += gridDim.x * blockDim.x) {
+        const double val = from_fix(acc[i]);
+        acc[i] = 0;
+        const int k = i / (12 * B), e = i - k * 12 * B;
+        (k == 0 ? a.g_P0 : a.g_P1)[e] = (float)val;
     }
 }
 
@@ -403,6 +397,7 @@ cudaError_t launch_f1_backward(const F1Args& a, cudaStream_t stream) {
     }
     dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, a.B);
     f1_bwd_kernel<<<grid, NT, sizeof(BwdSmem), stream>>>(a);
+    f1_bwd_finalize_kernel<<<(24 * a.B + 255) / 256, 256, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
