@@ -135,6 +135,24 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
     const float gout = a.gout ? __ldg(a.gout) : 1.0f;
     const Geo g = make_geo(H, W);
 
+    const float* dispb = a.disp + (size_t)b * HW;
+    const float* tgtb = a.tgt + (size_t)b * 3 * HW;
+    const int HWi = H * W;
+    // disparity and target of a halo position (reflection-padded, clamped): the loads of the NEXT position of this thread are issued
+    // before the projections and gathers of the current one (and the first ones before the barrier below), so that their latency is
+    // not the first thing every iteration of phase 1 waits for
+    auto pix_of = [&](int p) {
+        const int hy = p / W2, hx = p - hy * W2;
+        const int y = clampi(reflect1(ty0 - 2 + hy, H), 0, H - 1), x = clampi(reflect1(tx0 - 2 + hx, W), 0, W - 1);
+        return y * W + x;
+    };
+    float d_nx, tv_nx[3];
+    {
+        const int i = pix_of(tid);   // NT <= H2 * W2: every thread has a first position
+        d_nx = __ldg(dispb + i);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tv_nx[c] = __ldg(tgtb + (i + c * HWi));
+    }
     if (tid < 12) sm.cst[tid] = a.inv_K[16 * b + tid];
     else if (tid < 24) sm.cst[tid] = a.P0[12 * b + tid - 12];
     else if (tid < 36) sm.cst[tid] = a.P1[12 * b + tid - 24];
@@ -154,13 +172,10 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
     }
     __syncthreads();
 
-    const float* dispb = a.disp + (size_t)b * HW;
-    const float* tgtb = a.tgt + (size_t)b * 3 * HW;
     const float* s0b = a.src0 + (size_t)b * 3 * HW;
     const float* s1b = a.src1 + (size_t)b * 3 * HW;
     const uint8_t* __restrict__ idxb = a.idx + (size_t)b * HW;
     const float* __restrict__ mkb = a.mask ? a.mask + (size_t)b * HW : nullptr;
-    const int HWi = H * W;
 
     // ---------------- phase 1 ---------------------------------------------------------------------------------
     {
@@ -171,10 +186,16 @@ __global__ void __launch_bounds__(NT, 2) f1_bwd_kernel(const F1Args a) {
             int ry = ty0 - 2 + hy, rx = tx0 - 2 + hx;
             int y = clampi(reflect1(ry, H), 0, H - 1), x = clampi(reflect1(rx, W), 0, W - 1);
             const int i = y * W + x;
-            float d = __ldg(dispb + i);
+            const float d = d_nx;
             float tv[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) tv[c] = __ldg(tgtb + (i + c * HWi));
+            for (int c = 0; c < 3; ++c) tv[c] = tv_nx[c];
+            if (p + NT < H2 * W2) {
+                const int in = pix_of(p + NT);
+                d_nx = __ldg(dispb + in);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) tv_nx[c] = __ldg(tgtb + (in + c * HWi));
+            }
             float depth = depth_bwd(d, a.min_disp, a.disp_range);
             float cr[3], X[3], pr[3], rz;
             cam_ray(sm.cst, (float)x, (float)y, cr);
